@@ -1,0 +1,176 @@
+/* zkr.h -- C ABI of the B200-native BN254 Groth16 prover for simple-zk-rollups.
+ *
+ * This is the drop-in boundary for the proof-generation hot path of
+ * kendricktan/simple-zk-rollups.  Each entry point replaces one call the reference makes
+ * into its (un-vendored) websnark / snarkjs dependencies; citations are relative to the
+ * reference tree:
+ *
+ *   zkr_ctx_create        <-> buildBn128()                    operator/src/snarks/common.ts:23
+ *   zkr_pkey_load_bin     <-> consumes binarifyProvingKey()   operator/src/utils/binarify.ts:50-207
+ *                             output; done ONCE per circuit instead of per proof (common.ts:28)
+ *   zkr_prove             <-> wasmBn128.groth16GenProof(witnessBin, provingKeyBin)
+ *                                                             operator/src/snarks/common.ts:29
+ *                             witnessBin = binarifyWitness()  operator/src/utils/binarify.ts:10-48
+ *   zkr_prove_batch       <-> many independent genTxVerifierProof calls (tx.ts:6-10), one per GPU
+ *   zkr_msm_* / zkr_ntt   <-> websnark g1_multiexp / g2_multiexp / fft_* (inside groth16GenProof);
+ *                             exported for the standalone sweeps of BASELINE.json configs[2..3]
+ *   zkr_synth_setup       <-> `snarkjs setup --protocol groth`  prover/package.json:34,37
+ *                             (synthetic keys only: toxic waste is an input)
+ *
+ * Conventions
+ *   - All multi-byte integers little-endian.  Field elements are 32 bytes = 8 x u32 limbs,
+ *     least-significant first (binarify.ts:68-76).
+ *   - "Fq-M"/"Fr-M" = Montgomery form, radix 2^256 (binarify.ts:78-90); "std" = plain value.
+ *   - Every function returns 0 on success or a negative ZKR_E_* code; zkr_last_error()
+ *     returns a thread-local message.  There is NO CPU fallback: without a usable sm_100
+ *     device every compute entry point fails with ZKR_E_NO_DEVICE / ZKR_E_CUDA.
+ *   - Input buffers are borrowed for the duration of the call; outputs are caller-allocated.
+ *     zkr_ctx / zkr_pkey / zkr_bases are opaque handles owned by the library until freed.
+ *   - Calls on one zkr_ctx are serialised by the caller (one ctx per thread / per GPU).
+ */
+#ifndef ZKR_H
+#define ZKR_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZKR_OK 0
+#define ZKR_E_INVALID (-1)        /* bad argument */
+#define ZKR_E_BADKEY (-2)         /* proving-key buffer fails structural validation */
+#define ZKR_E_WITNESS_RANGE (-3)  /* a witness / scalar value is >= r, or witness[0] != 1 */
+#define ZKR_E_CUDA (-4)           /* CUDA runtime error (message has the detail) */
+#define ZKR_E_NO_DEVICE (-5)      /* no CUDA device / not an sm_100 part */
+#define ZKR_E_NOMEM (-6)
+#define ZKR_E_NCCL (-7)
+#define ZKR_E_UNSUPPORTED (-8)
+
+#define ZKR_PROOF_BYTES 256
+
+typedef struct zkr_ctx zkr_ctx;
+typedef struct zkr_pkey zkr_pkey;
+typedef struct zkr_bases zkr_bases;
+
+/* Per-stage device times of the last zkr_prove on this ctx, milliseconds (CUDA events). */
+typedef struct zkr_stats {
+    float total_ms;      /* first kernel launch .. proof bytes on host */
+    float h2d_ms;        /* witness upload */
+    float lc_ms;         /* sparse A_T, B_T */
+    float ntt_ms;        /* H pipeline (6 NTTs + pointwise) */
+    float msm_a_ms, msm_b1_ms, msm_b2_ms, msm_c_ms, msm_h_ms;
+    float assemble_ms;
+    uint64_t kernel_launches; /* kernels of this library launched by the call */
+} zkr_stats;
+
+const char* zkr_strerror(int code);
+const char* zkr_last_error(void);
+/* library / build identification, e.g. "zkr 0.1 sm_100a" */
+const char* zkr_version(void);
+
+/* ---- context ------------------------------------------------------------------------ */
+int zkr_ctx_create(int device, zkr_ctx** out);
+void zkr_ctx_destroy(zkr_ctx* ctx);
+/* Order all subsequent work of this ctx after / before `stream` (a cudaStream_t, may be
+ * NULL = legacy default stream): the library forks its internal streams off it and joins
+ * them back, so CUDA events recorded on `stream` bracket the library's kernels. */
+int zkr_ctx_set_stream(zkr_ctx* ctx, void* stream);
+int zkr_ctx_synchronize(zkr_ctx* ctx);
+/* number of this library's kernels launched through ctx since creation */
+uint64_t zkr_ctx_kernel_launches(const zkr_ctx* ctx);
+
+/* ---- proving key -------------------------------------------------------------------- */
+/* Parse the websnark binary proving key (binarify.ts:152-202 layout), convert
+ * polsA/polsB to row-major CSR, compact + window-precompute the five base sets, keep all of it
+ * resident in HBM.  buf may be host memory; it is not referenced after return. */
+int zkr_pkey_load_bin(zkr_ctx* ctx, const void* buf, size_t len, zkr_pkey** out);
+void zkr_pkey_free(zkr_pkey* pk);
+int zkr_pkey_info(const zkr_pkey* pk, uint32_t* n_vars, uint32_t* n_public, uint32_t* domain_size,
+                  uint64_t* device_bytes);
+
+/* ---- prove -------------------------------------------------------------------------- */
+/* witness: n_signals x 32 B std form (binarifyWitness layout), HOST memory.
+ * r32 / s32: blinding scalars, 32 B std form < r, or NULL for 0 (the snarkjs debug mode;
+ *   production callers pass CSPRNG output -- websnark draws them internally).
+ * out_proof: 256 B = pi_a (x|y) | pi_b (x.c0|x.c1|y.c0|y.c1) | pi_c (x|y), std form, affine,
+ *   i.e. exactly the integers websnark prints as decimal strings (z omitted: "1" / ["1","0"]).
+ *   A point at infinity is encoded as all-zero coordinates. */
+int zkr_prove(zkr_ctx* ctx, const zkr_pkey* pk, const void* witness, size_t n_signals,
+              const void* r32, const void* s32, void* out_proof, zkr_stats* stats);
+/* Same with the witness already resident in device memory of ctx's GPU (d_witness) and the
+ * proof written to device memory (d_out_proof, 256 B); asynchronous w.r.t. the host, ordered
+ * on the ctx stream (zkr_ctx_set_stream). */
+int zkr_prove_dev(zkr_ctx* ctx, const zkr_pkey* pk, const void* d_witness, size_t n_signals,
+                  const void* r32, const void* s32, void* d_out_proof);
+/* n_proofs independent proofs over n_ctx contexts (one per GPU; pks[i] is the same key loaded on
+ * ctxs[i]'s device), scheduled round-robin, one in flight per GPU.  witnesses: n_proofs buffers. */
+int zkr_prove_batch(zkr_ctx* const* ctxs, const zkr_pkey* const* pks, int n_ctx,
+                    const void* const* witnesses, size_t n_signals, int n_proofs,
+                    const void* rs32 /* n_proofs x 64 B (r|s) or NULL */, void* out_proofs);
+
+/* ---- standalone MSM ----------------------------------------------------------------- */
+/* group: 1 = G1 (64 B affine Fq-M points), 2 = G2 (128 B, x.c0|x.c1|y.c0|y.c1).
+ * points: host memory, n of them; x == 0 marks infinity (skipped).  Builds the windowed
+ * precompute table in HBM (window_bits = 0 -> chosen from n). */
+int zkr_bases_load(zkr_ctx* ctx, int group, const void* points, size_t n, int window_bits,
+                   zkr_bases** out);
+void zkr_bases_free(zkr_bases* b);
+int zkr_bases_info(const zkr_bases* b, uint64_t* n_points, int* window_bits, int* n_windows,
+                   uint64_t* device_bytes);
+/* sum_i scalars[i] * points[i]; scalars n x 32 B std form (< r), host memory if scalars_on_device
+ * == 0 else device memory.  out: affine std form, 64 B (G1) or 128 B (G2), host memory. */
+int zkr_msm(zkr_ctx* ctx, const zkr_bases* b, const void* scalars, size_t n, int scalars_on_device,
+            void* out_affine);
+/* device-resident, asynchronous variant: result stays on the device as an XYZZ point
+ * (4 coordinates Fq-M / Fq2-M: 128 B for G1, 256 B for G2). */
+int zkr_msm_dev(zkr_ctx* ctx, const zkr_bases* b, const void* d_scalars, size_t n, void* d_out_xyzz);
+
+/* ---- standalone NTT over Fr ----------------------------------------------------------- */
+#define ZKR_NTT_FORWARD 0       /* evaluations on <omega_n>, natural order in and out          */
+#define ZKR_NTT_INVERSE 1       /* coefficients (includes the 1/n scaling)                      */
+#define ZKR_NTT_COSET_FORWARD 2 /* evaluations on g<omega_n>, g = omega_2n                      */
+#define ZKR_NTT_COSET_INVERSE 3
+/* data: 2^log_n x 32 B Fr std form, transformed in place; on_device selects host / device memory.
+ * omega_n = 5^((r-1)/n) (snarkjs PolField convention). */
+int zkr_ntt(zkr_ctx* ctx, void* data, int log_n, int mode, int on_device);
+/* The fused H pipeline of the prover (SURVEY.md B.4 method iv): a_t, b_t = A_T, B_T evaluations
+ * (2^log_m x 32 B std form, device memory, clobbered); h_out receives h_0..h_{m-1} std form in
+ * BIT-REVERSED order when bitrev_out != 0 (what the prover feeds to the hExps MSM) or natural order. */
+int zkr_h_from_evals_dev(zkr_ctx* ctx, void* d_a_t, void* d_b_t, int log_m, void* d_h_out, int bitrev_out);
+
+/* ---- synthetic trusted setup (test / benchmark keys only) ------------------------------ */
+/* R1CS in CSC-by-signal form with coefficients taken from a pool:
+ *   ptr_X[n_vars+1], row_X[nnz], cid_X[nnz] (u32), pool: n_pool x 32 B std form.
+ * polsA must already contain the input-consistency rows (snarkjs setup_groth.js).
+ * toxic: 5 x 32 B std form (tau, alpha, beta, gamma, delta).
+ * Writes the websnark binary proving key (binarify.ts layout) into pk_out (pk_cap bytes; call with
+ * pk_out == NULL to get the required size in *pk_len) and the verifying key as raw std-form affine
+ * points into vk_out: alfa1 (64) | beta2 (128) | gamma2 (128) | delta2 (128) | IC[n_public+1] (64 each). */
+typedef struct zkr_r1cs_csc {
+    uint32_t n_vars, n_public, n_constraints, domain_size, n_pool;
+    const uint32_t *ptr_a, *row_a, *cid_a;
+    const uint32_t *ptr_b, *row_b, *cid_b;
+    const uint32_t *ptr_c, *row_c, *cid_c;
+    const void* pool;
+} zkr_r1cs_csc;
+int zkr_synth_setup(zkr_ctx* ctx, const zkr_r1cs_csc* r1cs, const void* toxic, void* pk_out,
+                    size_t pk_cap, size_t* pk_len, void* vk_out, size_t vk_cap);
+
+/* ---- test hooks (element-wise field / curve kernels; used by the parity tests) --------- */
+/* field: 0 = Fq, 1 = Fr.  op: 0 mul, 1 add, 2 sub, 3 sqr, 4 inverse, 5 to_mont, 6 from_mont.
+ * a, b, out: n x 32 B host buffers (Montgomery form operands for mul/add/sub/sqr/inverse). */
+int zkr_test_field_op(zkr_ctx* ctx, int field, int op, const void* a, const void* b, void* out, size_t n);
+/* group 1/2.  op: 0 = affine+affine (via XYZZ mixed add), 1 = double, 2 = scalar mul by k[i] (32 B std),
+ * 3 = xyzz full add of (P+P) and Q (exercises add()).  Points: affine Montgomery, x == 0 = infinity;
+ * out affine Montgomery. */
+int zkr_test_curve_op(zkr_ctx* ctx, int group, int op, const void* p, const void* q_or_k, void* out, size_t n);
+/* integer-pipe microbenchmarks: which: 0 = IMAD chain, 1 = IMAD.WIDE chain, 2 = Fq modmul chain,
+ * 3 = XYZZ mixed-add chain.  Returns operations per second (IMADs / modmuls / madds) in *ops_per_s. */
+int zkr_microbench(zkr_ctx* ctx, int which, int iters, double* ops_per_s, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZKR_H */

@@ -1,0 +1,142 @@
+// libzkr context / error plumbing (C-ABI: zkr_ctx_*, zkr_strerror, zkr_last_error, zkr_version).
+// zkr_ctx_create stands where the reference calls buildBn128()
+// (/root/reference/operator/src/snarks/common.ts:23) -- but it is created once, not per proof.
+#include "common.cuh"
+
+namespace zkr {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    set_error("CUDA error %d (%s) at %s:%d in %s", (int)e, cudaGetErrorString(e), file, line, what);
+    if (e == cudaErrorMemoryAllocation) return ZKR_E_NOMEM;
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return ZKR_E_NO_DEVICE;
+    return ZKR_E_CUDA;
+}
+
+void ntt_tables_free(NttTables* t);   // ntt.cu
+
+}  // namespace zkr
+
+using namespace zkr;
+
+extern "C" const char* zkr_strerror(int code) {
+    switch (code) {
+        case ZKR_OK: return "ok";
+        case ZKR_E_INVALID: return "invalid argument";
+        case ZKR_E_BADKEY: return "malformed proving key";
+        case ZKR_E_WITNESS_RANGE: return "witness value out of range";
+        case ZKR_E_CUDA: return "CUDA error";
+        case ZKR_E_NO_DEVICE: return "no usable CUDA device (this library has no CPU fallback)";
+        case ZKR_E_NOMEM: return "out of device memory";
+        case ZKR_E_NCCL: return "NCCL error";
+        case ZKR_E_UNSUPPORTED: return "unsupported";
+        default: return "unknown error";
+    }
+}
+
+extern "C" const char* zkr_last_error(void) { return g_err; }
+
+extern "C" const char* zkr_version(void) { return "zkr 0.1 (BN254 Groth16, sm_100a)"; }
+
+extern "C" int zkr_ctx_create(int device, zkr_ctx** out) {
+    if (!out) return ZKR_E_INVALID;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        set_error("no CUDA device visible (%s); libzkr has no CPU fallback",
+                  e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return ZKR_E_NO_DEVICE;
+    }
+    if (device < 0 || device >= count) {
+        set_error("device %d out of range (0..%d)", device, count - 1);
+        return ZKR_E_INVALID;
+    }
+    cudaDeviceProp prop;
+    ZKR_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("device %d is sm_%d%d; this build only carries sm_100a code", device, prop.major, prop.minor);
+        return ZKR_E_NO_DEVICE;
+    }
+    DeviceGuard g(device);
+    zkr_ctx* c = new zkr_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    for (int i = 0; i < kNumStreams; i++) {
+        ZKR_CUDA(cudaStreamCreateWithFlags(&c->s[i], cudaStreamNonBlocking));
+        ZKR_CUDA(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
+    }
+    ZKR_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    *out = c;
+    return ZKR_OK;
+}
+
+extern "C" void zkr_ctx_destroy(zkr_ctx* c) {
+    if (!c) return;
+    DeviceGuard g(c->device);
+    cudaDeviceSynchronize();
+    for (auto& kv : c->ntt) ntt_tables_free(kv.second);
+    for (auto& kv : c->scratch) cudaFree(kv.second.p);
+    for (int i = 0; i < kNumStreams; i++) {
+        cudaStreamDestroy(c->s[i]);
+        cudaEventDestroy(c->ev_join[i]);
+    }
+    cudaEventDestroy(c->ev_fork);
+    delete c;
+}
+
+extern "C" int zkr_ctx_set_stream(zkr_ctx* c, void* stream) {
+    if (!c) return ZKR_E_INVALID;
+    c->user_stream = (cudaStream_t)stream;
+    return ZKR_OK;
+}
+
+extern "C" int zkr_ctx_synchronize(zkr_ctx* c) {
+    if (!c) return ZKR_E_INVALID;
+    DeviceGuard g(c->device);
+    ZKR_CUDA(cudaStreamSynchronize(c->user_stream));
+    for (int i = 0; i < kNumStreams; i++) ZKR_CUDA(cudaStreamSynchronize(c->s[i]));
+    return ZKR_OK;
+}
+
+extern "C" uint64_t zkr_ctx_kernel_launches(const zkr_ctx* c) { return c ? c->launches : 0; }
+
+int zkr_ctx::scratch_get(const char* name, size_t bytes, void** out) {
+    DevBuf& b = scratch[name];
+    if (b.cap < bytes) {
+        if (b.p) {
+            // the old buffer may still be in use by queued work
+            ZKR_CUDA(cudaDeviceSynchronize());
+            ZKR_CUDA(cudaFree(b.p));
+            b.p = nullptr;
+            b.cap = 0;
+        }
+        size_t cap = (bytes + 255) & ~size_t(255);
+        ZKR_CUDA(cudaMalloc(&b.p, cap));
+        b.cap = cap;
+    }
+    *out = b.p;
+    return ZKR_OK;
+}
+
+int zkr_ctx::fork(int n) {
+    ZKR_CUDA(cudaEventRecord(ev_fork, user_stream));
+    for (int i = 0; i < n; i++) ZKR_CUDA(cudaStreamWaitEvent(s[i], ev_fork, 0));
+    return ZKR_OK;
+}
+
+int zkr_ctx::join(int n) {
+    for (int i = 0; i < n; i++) {
+        ZKR_CUDA(cudaEventRecord(ev_join[i], s[i]));
+        ZKR_CUDA(cudaStreamWaitEvent(user_stream, ev_join[i], 0));
+    }
+    return ZKR_OK;
+}

@@ -1,0 +1,379 @@
+// BN254 Fq / Fr Montgomery arithmetic on 8 x 32-bit limbs for sm_100a.
+//
+// Replaces the snarkjs bigInt / ZqField and websnark WASM f1m_* inner loops that
+// /root/reference/operator/src/snarks/common.ts:29 (groth16GenProof) runs on the CPU.
+// Representation matches the wire format of /root/reference/operator/src/utils/binarify.ts:68-90:
+// little-endian limbs, Montgomery radix 2^256, values fully reduced to [0, p).
+//
+// Multiplication is an 8x8 CIOS split into an "even" and an "odd" accumulator so that every
+// 32x32->64 product lands 64-bit aligned and each row is one uninterrupted carry chain of
+// mad.lo.cc / madc.hi.cc pairs; ptxas fuses each pair into one IMAD.WIDE.U32(.X) with carry
+// predicate, i.e. 128 IMAD.WIDE + 8 IMAD per modmul (the "136 IMAD" of SURVEY.md 8(d)).
+#pragma once
+#include <cstdint>
+
+namespace zkr {
+
+struct FqParams {   // base field q (binarify.ts:80)
+    static __host__ __device__ __forceinline__ constexpr uint32_t mod(int i) {
+        constexpr uint32_t m[8] = {0xd87cfd47u, 0x3c208c16u, 0x6871ca8du, 0x97816a91u,
+                                   0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+        return m[i];
+    }
+    static constexpr uint32_t INV = 0xe4866389u;   // -q^-1 mod 2^32
+    // R mod q, R^2 mod q (R = 2^256)
+    static __host__ __device__ __forceinline__ constexpr uint32_t one(int i) {
+        constexpr uint32_t m[8] = {0xc58f0d9du, 0xd35d438du, 0xf5c70b3du, 0x0a78eb28u,
+                                   0x7879462cu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+        return m[i];
+    }
+    static __host__ __device__ __forceinline__ constexpr uint32_t r2(int i) {
+        constexpr uint32_t m[8] = {0x538afa89u, 0xf32cfc5bu, 0xd44501fbu, 0xb5e71911u,
+                                   0x0a417ff6u, 0x47ab1effu, 0xcab8351fu, 0x06d89f71u};
+        return m[i];
+    }
+};
+
+struct FrParams {   // scalar field r (binarify.ts:87)
+    static __host__ __device__ __forceinline__ constexpr uint32_t mod(int i) {
+        constexpr uint32_t m[8] = {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u,
+                                   0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+        return m[i];
+    }
+    static constexpr uint32_t INV = 0xefffffffu;   // -r^-1 mod 2^32
+    static __host__ __device__ __forceinline__ constexpr uint32_t one(int i) {
+        constexpr uint32_t m[8] = {0x4ffffffbu, 0xac96341cu, 0x9f60cd29u, 0x36fc7695u,
+                                   0x7879462eu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+        return m[i];
+    }
+    static __host__ __device__ __forceinline__ constexpr uint32_t r2(int i) {
+        constexpr uint32_t m[8] = {0xae216da7u, 0x1bb8e645u, 0xe35c59e3u, 0x53fe3ab1u,
+                                   0x53bb8085u, 0x8c49833du, 0x7f4e44a5u, 0x0216d0b1u};
+        return m[i];
+    }
+};
+
+// ------------------------------------------------------------------ carry-chain building blocks
+// acc[0..7] += {x0,x2,x4,x6} * k laid out 64-bit aligned; the carry out is added into *top.
+__device__ __forceinline__ void mad_row_carry(uint32_t* acc, uint32_t& top, uint32_t x0, uint32_t x2,
+                                              uint32_t x4, uint32_t x6, uint32_t k) {
+    asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+        "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+        "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+        "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+        "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+        "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+        "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+        "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]),
+          "+r"(acc[6]), "+r"(acc[7]), "+r"(top)
+        : "r"(x0), "r"(x2), "r"(x4), "r"(x6), "r"(k));
+}
+
+// same, carry out known to be zero (the odd accumulator never exceeds 256 bits)
+__device__ __forceinline__ void mad_row(uint32_t* acc, uint32_t x0, uint32_t x2, uint32_t x4,
+                                        uint32_t x6, uint32_t k) {
+    asm("mad.lo.cc.u32 %0, %8, %12, %0;\n\t"
+        "madc.hi.cc.u32 %1, %8, %12, %1;\n\t"
+        "madc.lo.cc.u32 %2, %9, %12, %2;\n\t"
+        "madc.hi.cc.u32 %3, %9, %12, %3;\n\t"
+        "madc.lo.cc.u32 %4, %10, %12, %4;\n\t"
+        "madc.hi.cc.u32 %5, %10, %12, %5;\n\t"
+        "madc.lo.cc.u32 %6, %11, %12, %6;\n\t"
+        "madc.hi.u32 %7, %11, %12, %7;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]),
+          "+r"(acc[6]), "+r"(acc[7])
+        : "r"(x0), "r"(x2), "r"(x4), "r"(x6), "r"(k));
+}
+
+// e0 += o[1] (carry into the chain); o <- (o >> 64) + {x1,x3,x5,x7} * k
+__device__ __forceinline__ void mad_row_shift(uint32_t& e0, uint32_t* o, uint32_t x1, uint32_t x3,
+                                              uint32_t x5, uint32_t x7, uint32_t k) {
+    asm("add.cc.u32 %0, %0, %2;\n\t"
+        "madc.lo.cc.u32 %1, %9, %13, %3;\n\t"
+        "madc.hi.cc.u32 %2, %9, %13, %4;\n\t"
+        "madc.lo.cc.u32 %3, %10, %13, %5;\n\t"
+        "madc.hi.cc.u32 %4, %10, %13, %6;\n\t"
+        "madc.lo.cc.u32 %5, %11, %13, %7;\n\t"
+        "madc.hi.cc.u32 %6, %11, %13, %8;\n\t"
+        "madc.lo.cc.u32 %7, %12, %13, 0;\n\t"
+        "madc.hi.u32 %8, %12, %13, 0;"
+        : "+r"(e0), "+r"(o[0]), "+r"(o[1]), "+r"(o[2]), "+r"(o[3]), "+r"(o[4]), "+r"(o[5]),
+          "+r"(o[6]), "+r"(o[7])
+        : "r"(x1), "r"(x3), "r"(x5), "r"(x7), "r"(k));
+}
+
+__device__ __forceinline__ void mul_row(uint32_t* acc, uint32_t x0, uint32_t x2, uint32_t x4,
+                                        uint32_t x6, uint32_t k) {
+    asm("mul.lo.u32 %0, %8, %12;\n\t"
+        "mul.hi.u32 %1, %8, %12;\n\t"
+        "mul.lo.u32 %2, %9, %12;\n\t"
+        "mul.hi.u32 %3, %9, %12;\n\t"
+        "mul.lo.u32 %4, %10, %12;\n\t"
+        "mul.hi.u32 %5, %10, %12;\n\t"
+        "mul.lo.u32 %6, %11, %12;\n\t"
+        "mul.hi.u32 %7, %11, %12;"
+        : "=r"(acc[0]), "=r"(acc[1]), "=r"(acc[2]), "=r"(acc[3]), "=r"(acc[4]), "=r"(acc[5]),
+          "=r"(acc[6]), "=r"(acc[7])
+        : "r"(x0), "r"(x2), "r"(x4), "r"(x6), "r"(k));
+}
+
+template <class P>
+__device__ __forceinline__ void mont_row(uint32_t* e, uint32_t* o, const uint32_t* a, uint32_t bi, bool first) {
+    if (first) {
+        mul_row(o, a[1], a[3], a[5], a[7], bi);
+        mul_row(e, a[0], a[2], a[4], a[6], bi);
+    } else {
+        mad_row_shift(e[0], o, a[1], a[3], a[5], a[7], bi);
+        mad_row_carry(e, o[7], a[0], a[2], a[4], a[6], bi);
+    }
+    uint32_t mi = e[0] * P::INV;
+    mad_row(o, P::mod(1), P::mod(3), P::mod(5), P::mod(7), mi);
+    mad_row_carry(e, o[7], P::mod(0), P::mod(2), P::mod(4), P::mod(6), mi);
+}
+
+// r = r - p if r >= p
+template <class P>
+__device__ __forceinline__ void final_sub(uint32_t* r) {
+    uint32_t t[8], borrow;
+    asm("sub.cc.u32 %0, %9, %17;\n\t"
+        "subc.cc.u32 %1, %10, %18;\n\t"
+        "subc.cc.u32 %2, %11, %19;\n\t"
+        "subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\t"
+        "subc.cc.u32 %5, %14, %22;\n\t"
+        "subc.cc.u32 %6, %15, %23;\n\t"
+        "subc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32 %8, 0, 0;"
+        : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]),
+          "=r"(t[7]), "=r"(borrow)
+        : "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(P::mod(0)), "r"(P::mod(1)), "r"(P::mod(2)), "r"(P::mod(3)), "r"(P::mod(4)),
+          "r"(P::mod(5)), "r"(P::mod(6)), "r"(P::mod(7)));
+#pragma unroll
+    for (int i = 0; i < 8; i++) r[i] = borrow ? r[i] : t[i];
+}
+
+template <class P>
+__device__ __forceinline__ void mont_mul_raw(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+    uint32_t even[8], odd[8];
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+        mont_row<P>(even, odd, a, b[i], i == 0);
+        mont_row<P>(odd, even, a, b[i + 1], false);
+    }
+    asm("add.cc.u32 %0, %0, %8;\n\t"
+        "addc.cc.u32 %1, %1, %9;\n\t"
+        "addc.cc.u32 %2, %2, %10;\n\t"
+        "addc.cc.u32 %3, %3, %11;\n\t"
+        "addc.cc.u32 %4, %4, %12;\n\t"
+        "addc.cc.u32 %5, %5, %13;\n\t"
+        "addc.cc.u32 %6, %6, %14;\n\t"
+        "addc.u32 %7, %7, 0;"
+        : "+r"(even[0]), "+r"(even[1]), "+r"(even[2]), "+r"(even[3]), "+r"(even[4]), "+r"(even[5]),
+          "+r"(even[6]), "+r"(even[7])
+        : "r"(odd[1]), "r"(odd[2]), "r"(odd[3]), "r"(odd[4]), "r"(odd[5]), "r"(odd[6]), "r"(odd[7]));
+    final_sub<P>(even);
+#pragma unroll
+    for (int i = 0; i < 8; i++) r[i] = even[i];
+}
+
+// ------------------------------------------------------------------ field element
+template <class P>
+struct Fp {
+    uint32_t v[8];
+
+    static __device__ __forceinline__ Fp zero() {
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < 8; i++) r.v[i] = 0;
+        return r;
+    }
+    static __device__ __forceinline__ Fp one() {   // Montgomery 1
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < 8; i++) r.v[i] = P::one(i);
+        return r;
+    }
+    static __device__ __forceinline__ Fp r2() {
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < 8; i++) r.v[i] = P::r2(i);
+        return r;
+    }
+    __device__ __forceinline__ bool is_zero() const {
+        uint32_t x = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) x |= v[i];
+        return x == 0;
+    }
+    __device__ __forceinline__ bool operator==(const Fp& o) const {
+        uint32_t x = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) x |= v[i] ^ o.v[i];
+        return x == 0;
+    }
+    __device__ __forceinline__ bool operator!=(const Fp& o) const { return !(*this == o); }
+
+    friend __device__ __forceinline__ Fp operator*(const Fp& a, const Fp& b) {
+        Fp r;
+        mont_mul_raw<P>(r.v, a.v, b.v);
+        return r;
+    }
+    __device__ __forceinline__ Fp sqr() const { return *this * *this; }
+
+    friend __device__ __forceinline__ Fp operator+(const Fp& a, const Fp& b) {
+        Fp r;
+        asm("add.cc.u32 %0, %8, %16;\n\t"
+            "addc.cc.u32 %1, %9, %17;\n\t"
+            "addc.cc.u32 %2, %10, %18;\n\t"
+            "addc.cc.u32 %3, %11, %19;\n\t"
+            "addc.cc.u32 %4, %12, %20;\n\t"
+            "addc.cc.u32 %5, %13, %21;\n\t"
+            "addc.cc.u32 %6, %14, %22;\n\t"
+            "addc.u32 %7, %15, %23;"
+            : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]),
+              "=r"(r.v[6]), "=r"(r.v[7])
+            : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]),
+              "r"(a.v[6]), "r"(a.v[7]), "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]),
+              "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+        final_sub<P>(r.v);
+        return r;
+    }
+    friend __device__ __forceinline__ Fp operator-(const Fp& a, const Fp& b) {
+        Fp r;
+        uint32_t borrow;
+        asm("sub.cc.u32 %0, %9, %17;\n\t"
+            "subc.cc.u32 %1, %10, %18;\n\t"
+            "subc.cc.u32 %2, %11, %19;\n\t"
+            "subc.cc.u32 %3, %12, %20;\n\t"
+            "subc.cc.u32 %4, %13, %21;\n\t"
+            "subc.cc.u32 %5, %14, %22;\n\t"
+            "subc.cc.u32 %6, %15, %23;\n\t"
+            "subc.cc.u32 %7, %16, %24;\n\t"
+            "subc.u32 %8, 0, 0;"
+            : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]),
+              "=r"(r.v[6]), "=r"(r.v[7]), "=r"(borrow)
+            : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]),
+              "r"(a.v[6]), "r"(a.v[7]), "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]),
+              "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+        // borrow is 0 or 0xffffffff: add back p & borrow
+        asm("add.cc.u32 %0, %0, %8;\n\t"
+            "addc.cc.u32 %1, %1, %9;\n\t"
+            "addc.cc.u32 %2, %2, %10;\n\t"
+            "addc.cc.u32 %3, %3, %11;\n\t"
+            "addc.cc.u32 %4, %4, %12;\n\t"
+            "addc.cc.u32 %5, %5, %13;\n\t"
+            "addc.cc.u32 %6, %6, %14;\n\t"
+            "addc.u32 %7, %7, %15;"
+            : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2]), "+r"(r.v[3]), "+r"(r.v[4]), "+r"(r.v[5]),
+              "+r"(r.v[6]), "+r"(r.v[7])
+            : "r"(P::mod(0) & borrow), "r"(P::mod(1) & borrow), "r"(P::mod(2) & borrow),
+              "r"(P::mod(3) & borrow), "r"(P::mod(4) & borrow), "r"(P::mod(5) & borrow),
+              "r"(P::mod(6) & borrow), "r"(P::mod(7) & borrow));
+        return r;
+    }
+    __device__ __forceinline__ Fp neg() const { return is_zero() ? *this : (zero() - *this); }
+    __device__ __forceinline__ Fp dbl() const { return *this + *this; }
+
+    // standard form <-> Montgomery
+    __device__ __forceinline__ Fp to_mont() const { return *this * r2(); }
+    __device__ __forceinline__ Fp from_mont() const {
+        Fp o = zero();
+        o.v[0] = 1;
+        return *this * o;
+    }
+    // a^(p-2); ~380 modmuls, used only O(1) times per proof / per setup element
+    __device__ Fp inverse() const {
+        Fp base = *this, acc = one();
+        uint32_t e[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) e[i] = P::mod(i);
+        e[0] -= 2;   // no borrow for either modulus (low limb >= 2)
+        for (int i = 0; i < 254; i++) {
+            if ((e[i >> 5] >> (i & 31)) & 1) acc = acc * base;
+            base = base.sqr();
+        }
+        return acc;
+    }
+    // is the standard-form value < p ?
+    __device__ __forceinline__ bool in_range() const {
+        uint32_t t[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) t[i] = v[i];
+        final_sub<P>(t);
+        bool same = true;
+#pragma unroll
+        for (int i = 0; i < 8; i++) same &= (t[i] == v[i]);
+        return same;   // unchanged by the conditional subtract  <=>  v < p
+    }
+
+    // 2 x 128-bit global memory access (callers guarantee 16-byte alignment)
+    static __device__ __forceinline__ Fp load(const void* p) {
+        const uint4* q = reinterpret_cast<const uint4*>(p);
+        uint4 a = q[0], b = q[1];
+        Fp r;
+        r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+        r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+        return r;
+    }
+    static __device__ __forceinline__ Fp load_ro(const void* p) {
+        const uint4* q = reinterpret_cast<const uint4*>(p);
+        uint4 a = __ldg(q), b = __ldg(q + 1);
+        Fp r;
+        r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+        r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+        return r;
+    }
+    __device__ __forceinline__ void store(void* p) const {
+        uint4* q = reinterpret_cast<uint4*>(p);
+        q[0] = make_uint4(v[0], v[1], v[2], v[3]);
+        q[1] = make_uint4(v[4], v[5], v[6], v[7]);
+    }
+};
+
+using Fq = Fp<FqParams>;
+using Fr = Fp<FrParams>;
+
+// ------------------------------------------------------------------ Fq2 = Fq[u]/(u^2+1)
+struct Fq2 {
+    Fq c0, c1;
+    static __device__ __forceinline__ Fq2 zero() { return {Fq::zero(), Fq::zero()}; }
+    static __device__ __forceinline__ Fq2 one() { return {Fq::one(), Fq::zero()}; }
+    __device__ __forceinline__ bool is_zero() const { return c0.is_zero() && c1.is_zero(); }
+    __device__ __forceinline__ bool operator==(const Fq2& o) const { return c0 == o.c0 && c1 == o.c1; }
+    __device__ __forceinline__ bool operator!=(const Fq2& o) const { return !(*this == o); }
+    friend __device__ __forceinline__ Fq2 operator+(const Fq2& a, const Fq2& b) { return {a.c0 + b.c0, a.c1 + b.c1}; }
+    friend __device__ __forceinline__ Fq2 operator-(const Fq2& a, const Fq2& b) { return {a.c0 - b.c0, a.c1 - b.c1}; }
+    // Karatsuba: 3 Fq modmuls
+    friend __device__ __forceinline__ Fq2 operator*(const Fq2& a, const Fq2& b) {
+        Fq t0 = a.c0 * b.c0, t1 = a.c1 * b.c1;
+        Fq t2 = (a.c0 + a.c1) * (b.c0 + b.c1);
+        return {t0 - t1, t2 - t0 - t1};
+    }
+    __device__ __forceinline__ Fq2 sqr() const {   // 2 modmuls
+        Fq t = c0 * c1;
+        return {(c0 + c1) * (c0 - c1), t + t};
+    }
+    __device__ __forceinline__ Fq2 neg() const { return {c0.neg(), c1.neg()}; }
+    __device__ __forceinline__ Fq2 dbl() const { return {c0.dbl(), c1.dbl()}; }
+    __device__ Fq2 inverse() const {
+        Fq n = (c0.sqr() + c1.sqr()).inverse();
+        return {c0 * n, (c1 * n).neg()};
+    }
+    __device__ __forceinline__ Fq2 to_mont() const { return {c0.to_mont(), c1.to_mont()}; }
+    __device__ __forceinline__ Fq2 from_mont() const { return {c0.from_mont(), c1.from_mont()}; }
+    static __device__ __forceinline__ Fq2 load(const void* p) {
+        return {Fq::load(p), Fq::load(reinterpret_cast<const char*>(p) + 32)};
+    }
+    static __device__ __forceinline__ Fq2 load_ro(const void* p) {
+        return {Fq::load_ro(p), Fq::load_ro(reinterpret_cast<const char*>(p) + 32)};
+    }
+    __device__ __forceinline__ void store(void* p) const {
+        c0.store(p);
+        c1.store(reinterpret_cast<char*>(p) + 32);
+    }
+};
+
+}  // namespace zkr

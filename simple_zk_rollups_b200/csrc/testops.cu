@@ -1,0 +1,203 @@
+// Element-wise test hooks and integer-pipe microbenchmarks (C-ABI: zkr_test_*, zkr_microbench).
+// These exist so the parity tests can drive the device field / curve arithmetic directly against
+// the CPU oracle, and so that roofline fractions can be quoted against a MEASURED IMAD peak
+// (MEASURED_PEAKS.json has none).
+#include "common.cuh"
+#include "ec.cuh"
+
+using namespace zkr;
+
+namespace {
+
+template <class F>
+__global__ void k_field_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    F x = F::load(a + 8 * i);
+    F y = b ? F::load(b + 8 * i) : F::zero();
+    F r;
+    switch (op) {
+        case 0: r = x * y; break;
+        case 1: r = x + y; break;
+        case 2: r = x - y; break;
+        case 3: r = x.sqr(); break;
+        case 4: r = x.inverse(); break;
+        case 5: r = x.to_mont(); break;
+        default: r = x.from_mont(); break;
+    }
+    r.store(out + 8 * i);
+}
+
+template <class F>
+__global__ void k_curve_op(int op, const char* p, const char* q, char* out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    constexpr size_t AB = 2 * sizeof(F);
+    Affine<F> P = Affine<F>::load(p + AB * i);
+    XYZZ<F> acc = XYZZ<F>::from_affine(P);
+    if (op == 0) {
+        Affine<F> Q = Affine<F>::load(q + AB * i);
+        if (!Q.is_inf()) acc.madd(Q);
+    } else if (op == 1) {
+        acc = acc.dbl();
+    } else if (op == 2) {
+        uint32_t k[8];
+        for (int j = 0; j < 8; j++) k[j] = reinterpret_cast<const uint32_t*>(q)[8 * i + j];
+        acc = scalar_mul(acc, k);
+    } else {
+        Affine<F> Q = Affine<F>::load(q + AB * i);
+        XYZZ<F> d = acc.dbl();
+        XYZZ<F> qq = XYZZ<F>::from_affine(Q);
+        qq = qq.dbl();           // non-trivial zz on both operands
+        d.add(qq);               // 2P + 2Q
+        acc = d;
+    }
+    acc.to_affine().store(out + AB * i);
+}
+
+__global__ void k_bench_imad(uint32_t* out, int iters, uint32_t a, uint32_t b) {
+    uint32_t x[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) x[j] = threadIdx.x + j;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[j]) : "r"(a), "r"(b));
+        }
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) s ^= x[j];
+    if (s == 0x12345678u) out[0] = s;
+}
+
+__global__ void k_bench_imad_wide(uint32_t* out, int iters, uint32_t b) {
+    unsigned long long x[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) x[j] = threadIdx.x + j;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                uint32_t lo = (uint32_t)x[j];
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(x[j]) : "r"(lo), "r"(b));
+            }
+        }
+    }
+    unsigned long long s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) s ^= x[j];
+    if (s == 0x12345678ull) out[0] = (uint32_t)s;
+}
+
+__global__ void k_bench_modmul(uint32_t* out, int iters) {
+    Fq x = Fq::one(), y = Fq::r2(), z = Fq::r2();
+    x.v[0] += threadIdx.x;
+    z.v[1] ^= threadIdx.x;
+    for (int it = 0; it < iters; it++) {
+        x = x * y;
+        z = z * y;
+    }
+    Fq s = x + z;
+    if (s.v[0] == 0x12345678u && s.v[7] == 1) out[0] = s.v[3];
+}
+
+__global__ void k_bench_madd(uint32_t* out, int iters) {
+    // acc = (1,2) generator; add 2G-affine-ish distinct point repeatedly: use P = G, acc starts at 2G
+    G1Affine g;
+    g.x = Fq::one();
+    g.y = Fq::one().dbl();
+    G1XYZZ acc = G1XYZZ::dbl_affine(g);
+    for (int it = 0; it < iters; it++) acc.madd(g);
+    if (acc.x.v[0] == 0x12345678u && acc.zz.v[7] == 1) out[0] = acc.y.v[3];
+}
+
+}  // namespace
+
+extern "C" int zkr_test_field_op(zkr_ctx* ctx, int field, int op, const void* a, const void* b, void* out, size_t n) {
+    if (!ctx || !a || !out || n == 0 || op < 0 || op > 6 || (field != 0 && field != 1)) return ZKR_E_INVALID;
+    if (op <= 2 && !b) return ZKR_E_INVALID;
+    DeviceGuard g(ctx->device);
+    uint32_t *da = nullptr, *db = nullptr, *dout = nullptr;
+    ZKR_CUDA(cudaMalloc(&da, n * 32));
+    ZKR_CUDA(cudaMalloc(&dout, n * 32));
+    ZKR_CUDA(cudaMemcpyAsync(da, a, n * 32, cudaMemcpyHostToDevice, ctx->s[0]));
+    if (b) {
+        ZKR_CUDA(cudaMalloc(&db, n * 32));
+        ZKR_CUDA(cudaMemcpyAsync(db, b, n * 32, cudaMemcpyHostToDevice, ctx->s[0]));
+    }
+    int grid = ceil_div(n, 128);
+    if (field == 0) ZKR_LAUNCH(ctx, k_field_op<Fq>, grid, 128, 0, ctx->s[0], op, da, db, dout, n);
+    else ZKR_LAUNCH(ctx, k_field_op<Fr>, grid, 128, 0, ctx->s[0], op, da, db, dout, n);
+    ZKR_CUDA(cudaMemcpyAsync(out, dout, n * 32, cudaMemcpyDeviceToHost, ctx->s[0]));
+    ZKR_CUDA(cudaStreamSynchronize(ctx->s[0]));
+    cudaFree(da);
+    cudaFree(db);
+    cudaFree(dout);
+    return ZKR_OK;
+}
+
+extern "C" int zkr_test_curve_op(zkr_ctx* ctx, int group, int op, const void* p, const void* q, void* out, size_t n) {
+    if (!ctx || !p || !out || n == 0 || op < 0 || op > 3 || (group != 1 && group != 2)) return ZKR_E_INVALID;
+    if (op != 1 && !q) return ZKR_E_INVALID;
+    DeviceGuard g(ctx->device);
+    size_t ab = group == 1 ? 64 : 128;
+    size_t qb = (op == 2) ? 32 : ab;
+    char *dp = nullptr, *dq = nullptr, *dout = nullptr;
+    ZKR_CUDA(cudaMalloc(&dp, n * ab));
+    ZKR_CUDA(cudaMalloc(&dout, n * ab));
+    ZKR_CUDA(cudaMemcpyAsync(dp, p, n * ab, cudaMemcpyHostToDevice, ctx->s[0]));
+    if (q) {
+        ZKR_CUDA(cudaMalloc(&dq, n * qb));
+        ZKR_CUDA(cudaMemcpyAsync(dq, q, n * qb, cudaMemcpyHostToDevice, ctx->s[0]));
+    }
+    int grid = ceil_div(n, 64);
+    if (group == 1) ZKR_LAUNCH(ctx, k_curve_op<Fq>, grid, 64, 0, ctx->s[0], op, dp, dq, dout, n);
+    else ZKR_LAUNCH(ctx, k_curve_op<Fq2>, grid, 64, 0, ctx->s[0], op, dp, dq, dout, n);
+    ZKR_CUDA(cudaMemcpyAsync(out, dout, n * ab, cudaMemcpyDeviceToHost, ctx->s[0]));
+    ZKR_CUDA(cudaStreamSynchronize(ctx->s[0]));
+    cudaFree(dp);
+    cudaFree(dq);
+    cudaFree(dout);
+    return ZKR_OK;
+}
+
+extern "C" int zkr_microbench(zkr_ctx* ctx, int which, int iters, double* ops_per_s, float* ms_out) {
+    if (!ctx || which < 0 || which > 3 || iters <= 0 || !ops_per_s) return ZKR_E_INVALID;
+    DeviceGuard g(ctx->device);
+    uint32_t* dout = nullptr;
+    ZKR_CUDA(cudaMalloc(&dout, 64));
+    cudaEvent_t e0, e1;
+    ZKR_CUDA(cudaEventCreate(&e0));
+    ZKR_CUDA(cudaEventCreate(&e1));
+    const int threads = 256;
+    const int blocks = ctx->sm_count * 4;   // 32 warps / SM
+    double per_thread = 0;
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {     // rep 0 = warm-up
+        ZKR_CUDA(cudaEventRecord(e0, ctx->s[0]));
+        switch (which) {
+            case 0: ZKR_LAUNCH(ctx, k_bench_imad, blocks, threads, 0, ctx->s[0], dout, iters, 0x9e3779b9u, 12345u);
+                per_thread = 32.0 * iters; break;
+            case 1: ZKR_LAUNCH(ctx, k_bench_imad_wide, blocks, threads, 0, ctx->s[0], dout, iters, 0x9e3779b9u);
+                per_thread = 32.0 * iters; break;
+            case 2: ZKR_LAUNCH(ctx, k_bench_modmul, blocks, threads, 0, ctx->s[0], dout, iters);
+                per_thread = 2.0 * iters; break;
+            default: ZKR_LAUNCH(ctx, k_bench_madd, blocks, threads, 0, ctx->s[0], dout, iters);
+                per_thread = 1.0 * iters; break;
+        }
+        ZKR_CUDA(cudaEventRecord(e1, ctx->s[0]));
+        ZKR_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        ZKR_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    *ops_per_s = per_thread * threads * blocks / (best * 1e-3);
+    if (ms_out) *ms_out = best;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(dout);
+    return ZKR_OK;
+}

@@ -1,0 +1,139 @@
+"""GPU parity: device Fq/Fr/G1/G2 arithmetic vs the Python-int oracle, bit-exact (integer work)."""
+import ctypes as C
+import random
+
+import numpy as np
+import pytest
+
+from oracle import bn254 as bn
+from simple_zk_rollups_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+MONT = 1 << 256
+
+
+def pack(vals):
+    return np.frombuffer(b"".join(int(v).to_bytes(32, "little") for v in vals), dtype=np.uint8).copy()
+
+
+def unpack(arr):
+    b = arr.tobytes()
+    return [int.from_bytes(b[i:i + 32], "little") for i in range(0, len(b), 32)]
+
+
+def edge_values(p, rng, n):
+    ed = [0, 1, 2, p - 1, p - 2, (p + 1) // 2, MONT % p, (MONT * MONT) % p, (1 << 253), (1 << 224) - 1]
+    return ed + [rng.randrange(p) for _ in range(n - len(ed))]
+
+
+@pytest.mark.parametrize("field,p", [(0, bn.Q), (1, bn.R)])
+def test_field_ops(zctx, field, p):
+    L = _lib.lib()
+    rng = random.Random(1234 + field)
+    n = 100000
+    a = edge_values(p, rng, n)
+    b = list(reversed(edge_values(p, rng, n)))
+    rng.shuffle(b)
+    # operands are interpreted as Montgomery residues: x*y*R^-1
+    rinv = pow(MONT, -1, p)
+    A, B = pack(a), pack(b)
+    out = np.zeros_like(A)
+    exp = {0: [x * y * rinv % p for x, y in zip(a, b)],
+           1: [(x + y) % p for x, y in zip(a, b)],
+           2: [(x - y) % p for x, y in zip(a, b)],
+           3: [x * x * rinv % p for x in a],
+           5: [x * MONT % p for x in a],
+           6: [x * rinv % p for x in a]}
+    for op, e in exp.items():
+        _lib.check(L.zkr_test_field_op(zctx, field, op, _lib.buf_ptr(A), _lib.buf_ptr(B), _lib.buf_ptr(out), n))
+        got = unpack(out)
+        bad = [i for i in range(n) if got[i] != e[i]]
+        assert not bad, "field %d op %d first mismatch at %d" % (field, op, bad[0])
+    # inverse on a smaller batch (Fermat, ~380 modmuls each); Montgomery: inv(xR) = x^-1 R
+    m = 2000
+    nz = [v if v else 1 for v in a[:m]]
+    A2 = pack(nz)
+    out2 = np.zeros_like(A2)
+    _lib.check(L.zkr_test_field_op(zctx, field, 4, _lib.buf_ptr(A2), None, _lib.buf_ptr(out2), m))
+    got = unpack(out2)
+    for x, g in zip(nz, got):
+        assert g == pow(x * rinv % p, -1, p) * MONT % p
+
+
+def _g1_pts(rng, n):
+    fb = bn.fixed_base(1)
+    return fb.mul_many([rng.randrange(1, bn.R) for _ in range(n)])
+
+
+def _g2_pts(rng, n):
+    fb = bn.fixed_base(2)
+    return fb.mul_many([rng.randrange(1, bn.R) for _ in range(n)])
+
+
+def pack_g1(pts):
+    return pack([c * MONT % bn.Q for p in pts for c in ((0, 0) if p is None else p)])
+
+
+def pack_g2(pts):
+    flat = []
+    for p in pts:
+        if p is None:
+            flat += [0, 0, 0, 0]
+        else:
+            flat += [p[0][0], p[0][1], p[1][0], p[1][1]]
+    return pack([c * MONT % bn.Q for c in flat])
+
+
+def unpack_g1(arr):
+    rinv = pow(MONT, -1, bn.Q)
+    v = [x * rinv % bn.Q for x in unpack(arr)]
+    return [None if (v[i] == 0 and v[i + 1] == 0) else (v[i], v[i + 1]) for i in range(0, len(v), 2)]
+
+
+def unpack_g2(arr):
+    rinv = pow(MONT, -1, bn.Q)
+    v = [x * rinv % bn.Q for x in unpack(arr)]
+    out = []
+    for i in range(0, len(v), 4):
+        out.append(None if not any(v[i:i + 4]) else ((v[i], v[i + 1]), (v[i + 2], v[i + 3])))
+    return out
+
+
+@pytest.mark.parametrize("group", [1, 2])
+def test_curve_ops(zctx, group):
+    L = _lib.lib()
+    rng = random.Random(99 + group)
+    n = 256
+    cur = bn.G1 if group == 1 else bn.G2
+    gen_pts = _g1_pts if group == 1 else _g2_pts
+    pk, up = (pack_g1, unpack_g1) if group == 1 else (pack_g2, unpack_g2)
+    P = gen_pts(rng, n)
+    Q = gen_pts(rng, n)
+    # exceptional cases: Q == P, Q == -P, P infinity, Q infinity
+    Q[0] = P[0]
+    Q[1] = cur.neg(P[1])
+    P[2] = None
+    Q[3] = None
+    P[4] = None
+    Q[4] = None
+    Pa, Qa = pk(P), pk(Q)
+    out = np.zeros_like(Pa)
+    _lib.check(L.zkr_test_curve_op(zctx, group, 0, _lib.buf_ptr(Pa), _lib.buf_ptr(Qa), _lib.buf_ptr(out), n))
+    assert up(out) == [cur.add(p, q) for p, q in zip(P, Q)]
+    _lib.check(L.zkr_test_curve_op(zctx, group, 1, _lib.buf_ptr(Pa), None, _lib.buf_ptr(out), n))
+    assert up(out) == [cur.add(p, p) for p in P]
+    _lib.check(L.zkr_test_curve_op(zctx, group, 3, _lib.buf_ptr(Pa), _lib.buf_ptr(Qa), _lib.buf_ptr(out), n))
+    assert up(out) == [cur.add(cur.add(p, p), cur.add(q, q)) for p, q in zip(P, Q)]
+    ks = [0, 1, 2, bn.R - 1, bn.R, (1 << 256) - 1] + [rng.randrange(bn.R) for _ in range(n - 6)]
+    K = pack(ks)
+    _lib.check(L.zkr_test_curve_op(zctx, group, 2, _lib.buf_ptr(Pa), _lib.buf_ptr(K), _lib.buf_ptr(out), n))
+    assert up(out) == [cur.mul(p, k) for p, k in zip(P, ks)]
+
+
+def test_microbench_runs(zctx):
+    L = _lib.lib()
+    ops = C.c_double()
+    ms = C.c_float()
+    for which, it in ((0, 20000), (1, 20000), (2, 2000), (3, 500)):
+        _lib.check(L.zkr_microbench(zctx, which, it, C.byref(ops), C.byref(ms)))
+        assert ops.value > 0

@@ -1,0 +1,27 @@
+#!/usr/bin/env python3
+"""Measure the integer-pipe peaks on the GPU box: IMAD, IMAD.WIDE,
+register-resident Fq modmul chain, XYZZ mixed-add chain.  Writes gpurun_out/microbench.json."""
+import ctypes as C
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from simple_zk_rollups_b200 import _lib
+
+L = _lib.lib()
+h = C.c_void_p()
+_lib.check(L.zkr_ctx_create(0, C.byref(h)))
+res = {}
+for name, which, iters in (("imad_per_s", 0, 100000), ("imad_wide_per_s", 1, 100000),
+                           ("fq_modmul_per_s", 2, 20000), ("g1_madd_per_s", 3, 3000)):
+    ops, ms = C.c_double(), C.c_float()
+    _lib.check(L.zkr_microbench(h, which, iters, C.byref(ops), C.byref(ms)))
+    res[name] = ops.value
+    res[name.replace("_per_s", "_ms")] = ms.value
+res["modmul_imad_equiv_per_s"] = res["fq_modmul_per_s"] * 136
+res["madd_modmul_equiv_per_s"] = res["g1_madd_per_s"] * 10
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(res, open("gpurun_out/microbench.json", "w"), indent=1)
+print(json.dumps(res))
+L.zkr_ctx_destroy(h)
