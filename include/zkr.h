@@ -81,6 +81,13 @@ int zkr_ctx_synchronize(zkr_ctx* ctx);
 /* number of this library's kernels launched through ctx since creation */
 uint64_t zkr_ctx_kernel_launches(const zkr_ctx* ctx);
 
+/* plain device-memory helpers on ctx's GPU (stream-ordered on the ctx stream; download synchronises).
+ * They let a host language without a CUDA binding stage "already resident" inputs. */
+int zkr_dev_malloc(zkr_ctx* ctx, size_t bytes, void** d_out);
+int zkr_dev_free(zkr_ctx* ctx, void* d_ptr);
+int zkr_dev_upload(zkr_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);
+int zkr_dev_download(zkr_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
+
 /* ---- proving key -------------------------------------------------------------------- */
 /* Parse the websnark binary proving key (binarify.ts:152-202 layout), convert
  * polsA/polsB to row-major CSR, compact + window-precompute the five base sets, keep all of it
@@ -132,6 +139,11 @@ int zkr_msm_dev(zkr_ctx* ctx, const zkr_bases* b, const void* d_scalars, size_t 
 #define ZKR_NTT_INVERSE 1       /* coefficients (includes the 1/n scaling)                      */
 #define ZKR_NTT_COSET_FORWARD 2 /* evaluations on g<omega_n>, g = omega_2n                      */
 #define ZKR_NTT_COSET_INVERSE 3
+/* OR-able order flags: skip the bit-reversal pass on one side.  BITREV_OUT: natural in, result left
+ * in bit-reversed order (pure DIF).  BITREV_IN: input given in bit-reversed order, natural out (pure
+ * DIT).  The prover chains DIF^-1 -> DIT -> DIF^-1 and never runs a bit-reversal pass. */
+#define ZKR_NTT_BITREV_OUT 0x10
+#define ZKR_NTT_BITREV_IN 0x20
 /* data: 2^log_n x 32 B Fr std form, transformed in place; on_device selects host / device memory.
  * omega_n = 5^((r-1)/n) (snarkjs PolField convention). */
 int zkr_ntt(zkr_ctx* ctx, void* data, int log_n, int mode, int on_device);

@@ -40,6 +40,10 @@ _SIGS = {
     "zkr_ctx_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "zkr_ctx_synchronize": (C.c_int, [C.c_void_p]),
     "zkr_ctx_kernel_launches": (C.c_uint64, [C.c_void_p]),
+    "zkr_dev_malloc": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "zkr_dev_free": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "zkr_dev_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "zkr_dev_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "zkr_pkey_load_bin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
     "zkr_pkey_free": (None, [C.c_void_p]),
     "zkr_pkey_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),

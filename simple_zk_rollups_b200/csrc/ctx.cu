@@ -140,3 +140,34 @@ int zkr_ctx::join(int n) {
     }
     return ZKR_OK;
 }
+
+extern "C" int zkr_dev_malloc(zkr_ctx* c, size_t bytes, void** d_out) {
+    if (!c || !d_out) return ZKR_E_INVALID;
+    DeviceGuard g(c->device);
+    ZKR_CUDA(cudaMalloc(d_out, bytes ? bytes : 1));
+    return ZKR_OK;
+}
+
+extern "C" int zkr_dev_free(zkr_ctx* c, void* d_ptr) {
+    if (!c) return ZKR_E_INVALID;
+    DeviceGuard g(c->device);
+    ZKR_CUDA(cudaStreamSynchronize(c->user_stream));
+    ZKR_CUDA(cudaFree(d_ptr));
+    return ZKR_OK;
+}
+
+extern "C" int zkr_dev_upload(zkr_ctx* c, void* d_dst, const void* h_src, size_t bytes) {
+    if (!c || !d_dst || !h_src) return ZKR_E_INVALID;
+    DeviceGuard g(c->device);
+    ZKR_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, c->user_stream));
+    ZKR_CUDA(cudaStreamSynchronize(c->user_stream));   // h_src may be pageable and short-lived
+    return ZKR_OK;
+}
+
+extern "C" int zkr_dev_download(zkr_ctx* c, void* h_dst, const void* d_src, size_t bytes) {
+    if (!c || !h_dst || !d_src) return ZKR_E_INVALID;
+    DeviceGuard g(c->device);
+    ZKR_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, c->user_stream));
+    ZKR_CUDA(cudaStreamSynchronize(c->user_stream));
+    return ZKR_OK;
+}

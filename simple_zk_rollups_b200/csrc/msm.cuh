@@ -1,0 +1,524 @@
+// Signed-digit bucketed Pippenger MSM over precomputed window tables, templated on the curve
+// (Fq -> G1, Fq2 -> G2).  Replaces websnark g1_multiexp / g2_multiexp (five calls inside
+// groth16GenProof, /root/reference/operator/src/snarks/common.ts:29) and the per-signal
+// G1.mulScalar / G2.mulScalar loop of snarkjs prover_groth.js.
+//
+// B200-first design (DESIGN.md "MSM"):
+//   * The bases are static per circuit, HBM is 180 GB: at key-load time every base P_i is expanded
+//     to its W window multiples 2^(c w) P_i (affine, Montgomery).  All windows then share ONE set of
+//     2^(c-1) buckets, there is no window-combine (no 254 serial doublings), and c can be larger
+//     than a per-window scheme allows (c = 20 at n = 2^20 -> 13 mixed adds per point instead of 16).
+//   * per MSM:  digits (signed, c bits)  ->  radix sort of (bucket, point-ref) pairs  ->
+//     chunked bucket accumulation  ->  block-level weighted bucket reduction.
+//   * accumulation is perfectly load balanced for ANY scalar distribution: thread t owns entries
+//     [tL, (t+1)L) of the bucket-sorted list, adds runs of equal bucket with XYZZ mixed adds, writes
+//     complete (interior) runs straight to their bucket and hands its first / last partial run to the
+//     next level, which applies the same algorithm to the (<= 2 per thread) boundary partials.  A
+//     bucket holding 3 % of all points (the {0,1} witness skew of the rollup circuit) simply spans
+//     many threads.
+//   * reduction sum_b (b+1) B_b: per-thread running sums over K consecutive buckets, then a block
+//     suffix-scan turns sum_l l*S_l into plain sums; one more single-block kernel finishes.
+#pragma once
+#include <cub/device/device_radix_sort.cuh>
+
+#include "common.cuh"
+#include "ec.cuh"
+
+namespace zkr {
+
+constexpr int kAccumThreads = 128;
+constexpr int kLevelLog = 4;          // boundary levels: 16 entries per thread
+constexpr uint32_t kNegBit = 0x80000000u;
+
+struct MsmPlan {
+    int c = 0, W = 0;
+    uint32_t nbuckets = 0;            // 2^(c-1); also the sentinel key of skipped (zero) digits
+    static MsmPlan choose(uint64_t n, int c_forced) {
+        MsmPlan p;
+        int best = 0;
+        double best_cost = 1e300;
+        for (int c = 4; c <= 23; c++) {
+            int W = (255 + c - 1) / c;
+            if ((uint64_t)W * n >= (1ull << 31)) continue;
+            double cost = 10.0 * (double)n * W + 56.0 * (double)(1u << (c - 1));
+            if (cost < best_cost) { best_cost = cost; best = c; }
+        }
+        p.c = c_forced > 0 ? c_forced : best;
+        p.W = (255 + p.c - 1) / p.c;
+        p.nbuckets = 1u << (p.c - 1);
+        return p;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// table[w * n + i] = 2^(c w) * P_i, affine Montgomery
+template <class F>
+__global__ void k_precompute(const char* __restrict__ pts, char* __restrict__ table, uint32_t n, int c, int W) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    constexpr size_t AB = 2 * sizeof(F);
+    Affine<F> p = Affine<F>::load(pts + AB * i);
+    p.store(table + AB * i);
+    XYZZ<F> acc = XYZZ<F>::from_affine(p);
+    for (int w = 1; w < W; w++) {
+        for (int d = 0; d < c; d++) acc = acc.dbl();
+        acc.to_affine().store(table + AB * ((size_t)w * n + i));
+    }
+}
+
+// keys[w n + i] = |digit| - 1 (or sentinel for 0), vals[w n + i] = (w n + i) | sign
+__global__ void k_digits(const uint32_t* __restrict__ scalars, const uint32_t* __restrict__ src_index, uint32_t n,
+                         int c, int W, uint32_t sentinel, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                         int* __restrict__ range_err) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t* sp = scalars + 8 * (size_t)(src_index ? src_index[i] : i);
+    Fr k = Fr::load_ro(sp);
+    if (!k.in_range()) *range_err = 1;
+    uint32_t carry = 0;
+    const uint32_t half = 1u << (c - 1), mask = (1u << c) - 1;
+    for (int w = 0; w < W; w++) {
+        int bit = w * c, limb = bit >> 5, sh = bit & 31;
+        uint32_t d = 0;
+        if (limb < 8) {
+            d = k.v[limb] >> sh;
+            if (sh + c > 32 && limb + 1 < 8) d |= k.v[limb + 1] << (32 - sh);
+        }
+        d = (d & mask) + carry;
+        uint32_t neg = 0;
+        carry = 0;
+        if (d > half) {
+            d = (1u << c) - d;
+            neg = kNegBit;
+            carry = 1;
+        }
+        uint32_t pos = (uint32_t)w * n + i;
+        keys[pos] = d ? d - 1 : sentinel;
+        vals[pos] = pos | neg;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// level 1: affine table entries -> bucket sums / boundary partials
+template <class F, bool PREFETCH>
+__global__ void __launch_bounds__(kAccumThreads)
+k_accum_affine(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint32_t total, int logL,
+               const char* __restrict__ table, XYZZ<F>* __restrict__ buckets, XYZZ<F>* __restrict__ bnd,
+               uint32_t* __restrict__ bnd_keys, uint32_t sentinel) {
+    extern __shared__ uint32_t sm[];
+    constexpr size_t AB = 2 * sizeof(F);
+    const int L = 1 << logL, LP = L + 1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t* sk = sm + warp * 2 * 32 * LP;
+    uint32_t* sv = sk + 32 * LP;
+    const size_t wchunk = (size_t)blockIdx.x * (kAccumThreads / 32) + warp;   // warp-sized group of chunks
+    const size_t wbase = wchunk * 32 * L;
+    for (int i = lane; i < 32 * L; i += 32) {
+        size_t e = wbase + i;
+        uint32_t kk = sentinel, vv = 0;
+        if (e < total) {
+            kk = keys[e];
+            vv = vals[e];
+        }
+        int r = i >> logL, ci = i & (L - 1);
+        sk[r * LP + ci] = kk;
+        sv[r * LP + ci] = vv;
+    }
+    __syncwarp();
+    const uint32_t* mk = sk + lane * LP;
+    const uint32_t* mv = sv + lane * LP;
+    const size_t t = wchunk * 32 + lane;
+
+    XYZZ<F> acc = XYZZ<F>::identity();
+    uint32_t cur = mk[0];
+    bool first_run = true;
+    uint32_t head_key = sentinel, tail_key = sentinel;
+    Affine<F> nxt;
+    bool have = cur < sentinel;
+    if (PREFETCH && have) nxt = Affine<F>::load_ro(table + AB * (size_t)(mv[0] & ~kNegBit));
+    for (int j = 0; j < L; j++) {
+        if (!have) break;
+        const uint32_t key = mk[j], v = mv[j];
+        Affine<F> p;
+        if (PREFETCH) p = nxt;
+        else p = Affine<F>::load_ro(table + AB * (size_t)(v & ~kNegBit));
+        have = (j + 1 < L) && (mk[j + 1] < sentinel);
+        if (PREFETCH && have) nxt = Affine<F>::load_ro(table + AB * (size_t)(mv[j + 1] & ~kNegBit));
+        if (key != cur) {
+            if (first_run) {
+                acc.store(bnd + 2 * t);
+                head_key = cur;
+                first_run = false;
+            } else {
+                acc.store(buckets + cur);
+            }
+            acc = XYZZ<F>::identity();
+            cur = key;
+        }
+        if (v & kNegBit) p.y = p.y.neg();
+        acc.madd(p);
+    }
+    if (cur < sentinel) {
+        if (first_run) {
+            acc.store(bnd + 2 * t);
+            head_key = cur;
+        } else {
+            acc.store(bnd + 2 * t + 1);
+            tail_key = cur;
+        }
+    }
+    bnd_keys[2 * t] = head_key;
+    bnd_keys[2 * t + 1] = tail_key;
+}
+
+// level >= 2: XYZZ partials (with sentinel holes) -> bucket sums / boundary partials
+template <class F>
+__global__ void __launch_bounds__(64)
+k_accum_xyzz(const uint32_t* __restrict__ in_keys, const XYZZ<F>* __restrict__ in_pts, uint32_t count, int logL,
+             XYZZ<F>* __restrict__ buckets, XYZZ<F>* __restrict__ bnd, uint32_t* __restrict__ bnd_keys,
+             uint32_t sentinel, bool final_level) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t begin = t << logL;
+    if (begin >= count) {
+        if (!final_level) {
+            // threads past the end still own boundary slots the next level will read
+            bnd_keys[2 * t] = sentinel;
+            bnd_keys[2 * t + 1] = sentinel;
+        }
+        return;
+    }
+    size_t end = begin + ((size_t)1 << logL);
+    if (end > count) end = count;
+    XYZZ<F> acc = XYZZ<F>::identity();
+    uint32_t cur = sentinel;
+    bool first_run = true;
+    uint32_t head_key = sentinel, tail_key = sentinel;
+    for (size_t e = begin; e < end; e++) {
+        const uint32_t key = in_keys[e];
+        if (key >= sentinel) continue;
+        if (cur == sentinel) cur = key;
+        if (key != cur) {
+            if (first_run && !final_level) {
+                acc.store(bnd + 2 * t);
+                head_key = cur;
+            } else {
+                acc.store(buckets + cur);
+            }
+            first_run = false;
+            acc = XYZZ<F>::identity();
+            cur = key;
+        }
+        acc.add(XYZZ<F>::load(in_pts + e));
+    }
+    if (cur < sentinel) {
+        if (final_level) {
+            acc.store(buckets + cur);
+        } else if (first_run) {
+            acc.store(bnd + 2 * t);
+            head_key = cur;
+        } else {
+            acc.store(bnd + 2 * t + 1);
+            tail_key = cur;
+        }
+    }
+    if (!final_level) {
+        bnd_keys[2 * t] = head_key;
+        bnd_keys[2 * t + 1] = tail_key;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// block-wide helpers on XYZZ points staged in shared memory (blockDim.x == NT, power of two)
+template <class F, int NT>
+__device__ __forceinline__ XYZZ<F> block_sum(XYZZ<F>* sp, const XYZZ<F>& mine, int skip_first) {
+    const int l = threadIdx.x;
+    sp[l] = (l < skip_first) ? XYZZ<F>::identity() : mine;
+    __syncthreads();
+    for (int d = NT / 2; d >= 1; d >>= 1) {
+        if (l < d) {
+            XYZZ<F> a = sp[l];
+            a.add(sp[l + d]);
+            sp[l] = a;
+        }
+        __syncthreads();
+    }
+    XYZZ<F> r = sp[0];
+    __syncthreads();
+    return r;
+}
+
+// inclusive suffix sums: returns T_l = sum_{l' >= l} v_l'
+template <class F, int NT>
+__device__ __forceinline__ XYZZ<F> block_suffix_scan(XYZZ<F>* sp, const XYZZ<F>& mine) {
+    const int l = threadIdx.x;
+    XYZZ<F> v = mine;
+    sp[l] = v;
+    __syncthreads();
+    for (int d = 1; d < NT; d <<= 1) {
+        XYZZ<F> o = XYZZ<F>::identity();
+        const bool has = l + d < NT;
+        if (has) o = sp[l + d];
+        __syncthreads();
+        if (has) {
+            v.add(o);
+            sp[l] = v;
+        }
+        __syncthreads();
+    }
+    return v;
+}
+
+template <class F>
+__device__ __forceinline__ XYZZ<F> mul_small(XYZZ<F> p, uint32_t k) {
+    XYZZ<F> acc = XYZZ<F>::identity();
+    while (k) {
+        if (k & 1) acc.add(p);
+        k >>= 1;
+        if (k) p = p.dbl();
+    }
+    return acc;
+}
+
+constexpr int kReduceThreads = 256;
+
+// stage 1: thread u owns buckets [uK, (u+1)K): running sums, then per block
+//   X_g = sum_l acc_l,  Y_g = sum_l l * S_l,  Z_g = sum_l S_l        (3 points per block)
+template <class F>
+__global__ void __launch_bounds__(kReduceThreads)
+k_reduce_stage1(const XYZZ<F>* __restrict__ buckets, uint32_t nbuckets, uint32_t K, XYZZ<F>* __restrict__ out) {
+    extern __shared__ unsigned char smraw[];
+    XYZZ<F>* sp = reinterpret_cast<XYZZ<F>*>(smraw);
+    const uint32_t u = blockIdx.x * kReduceThreads + threadIdx.x;
+    XYZZ<F> run = XYZZ<F>::identity(), acc = XYZZ<F>::identity();
+    const uint64_t b0 = (uint64_t)u * K;
+    for (int b = (int)K - 1; b >= 0; b--) {
+        if (b0 + b < nbuckets) {
+            run.add(XYZZ<F>::load(buckets + b0 + b));
+            acc.add(run);
+        }
+    }
+    XYZZ<F> X = block_sum<F, kReduceThreads>(sp, acc, 0);
+    XYZZ<F> T = block_suffix_scan<F, kReduceThreads>(sp, run);
+    __syncthreads();
+    XYZZ<F> Y = block_sum<F, kReduceThreads>(sp, T, 1);      // sum_{l>=1} T_l = sum_l l*S_l
+    if (threadIdx.x == 0) {
+        X.store(out + 3 * blockIdx.x);
+        Y.store(out + 3 * blockIdx.x + 1);
+        T.store(out + 3 * blockIdx.x + 2);                   // T_0 = Z_g
+    }
+}
+
+// stage 2 (one block of G <= 256 threads): total = sum X + K sum Y + 256 K sum_g g Z_g
+template <class F>
+__global__ void __launch_bounds__(kReduceThreads)
+k_reduce_stage2(const XYZZ<F>* __restrict__ in, uint32_t G, uint32_t K, XYZZ<F>* __restrict__ out) {
+    extern __shared__ unsigned char smraw[];
+    XYZZ<F>* sp = reinterpret_cast<XYZZ<F>*>(smraw);
+    const uint32_t g = threadIdx.x;
+    XYZZ<F> X = XYZZ<F>::identity(), Y = X, Z = X;
+    if (g < G) {
+        X = XYZZ<F>::load(in + 3 * g);
+        Y = XYZZ<F>::load(in + 3 * g + 1);
+        Z = XYZZ<F>::load(in + 3 * g + 2);
+    }
+    XYZZ<F> sx = block_sum<F, kReduceThreads>(sp, X, 0);
+    XYZZ<F> sy = block_sum<F, kReduceThreads>(sp, Y, 0);
+    XYZZ<F> tz = block_suffix_scan<F, kReduceThreads>(sp, Z);
+    __syncthreads();
+    XYZZ<F> sgz = block_sum<F, kReduceThreads>(sp, tz, 1);
+    if (threadIdx.x == 0) {
+        XYZZ<F> r = mul_small(sgz, kReduceThreads);
+        r.add(sy);
+        r = mul_small(r, K);
+        r.add(sx);
+        r.store(out);
+    }
+}
+
+// XYZZ (Montgomery) -> affine standard form bytes; identity -> zeros
+template <class F>
+__global__ void k_xyzz_to_affine_std(const XYZZ<F>* in, char* out) {
+    XYZZ<F> p = XYZZ<F>::load(in);
+    Affine<F> a = p.to_affine();
+    a.x.from_mont().store(out);
+    a.y.from_mont().store(out + sizeof(F));
+}
+
+// ------------------------------------------------------------------------------------------------
+struct MsmWork {                      // per-bases device work buffers
+    uint32_t *keys[2] = {nullptr, nullptr}, *vals[2] = {nullptr, nullptr};
+    void* cub_tmp = nullptr;
+    size_t cub_bytes = 0;
+    void* buckets = nullptr;
+    void* bnd[2] = {nullptr, nullptr};
+    uint32_t* bnd_keys[2] = {nullptr, nullptr};
+    void* red = nullptr;              // 3 * G points
+    void* result = nullptr;           // 1 XYZZ
+    int* range_err = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace zkr
+
+struct zkr_bases {
+    zkr_ctx* ctx = nullptr;
+    int group = 1;
+    uint64_t n_src = 0;               // points handed in (including infinities)
+    uint32_t n = 0;                   // after dropping infinities
+    uint32_t* src_index = nullptr;    // device, compact -> source index; null if identity
+    char* table = nullptr;            // device [W][n] affine Montgomery
+    zkr::MsmPlan plan;
+    zkr::MsmWork work;
+    size_t bytes = 0;
+    int logL = 5;
+    uint32_t T1p = 0;                 // level-1 threads (padded to whole blocks)
+};
+
+namespace zkr {
+
+template <class F>
+int bases_build(zkr_ctx* ctx, zkr_bases* b, const char* h_points, size_t n_src, int c_forced, cudaStream_t st);
+template <class F>
+int msm_run(zkr_ctx* ctx, cudaStream_t st, const zkr_bases* b, const uint32_t* d_scalars, XYZZ<F>* d_out);
+void bases_release(zkr_bases* b);
+
+// ---------------------------------------------------------------- implementation (header-only, two TUs)
+template <class F>
+int bases_build(zkr_ctx* ctx, zkr_bases* b, const char* h_points, size_t n_src, int c_forced, cudaStream_t st) {
+    constexpr size_t AB = 2 * sizeof(F);
+    constexpr size_t XB = 4 * sizeof(F);
+    b->ctx = ctx;
+    b->n_src = n_src;
+    // host-side compaction: x == 0 (all coordinate bytes zero) marks infinity (binarify.ts:92-95)
+    std::vector<uint32_t> idx;
+    idx.reserve(n_src);
+    for (size_t i = 0; i < n_src; i++) {
+        const uint64_t* x = reinterpret_cast<const uint64_t*>(h_points + AB * i);
+        uint64_t any = 0;
+        for (size_t j = 0; j < sizeof(F) / 8; j++) any |= x[j];
+        if (any) idx.push_back((uint32_t)i);
+    }
+    b->n = (uint32_t)idx.size();
+    const uint32_t n = b->n;
+    b->plan = MsmPlan::choose(n ? n : 1, c_forced);
+    const int W = b->plan.W;
+    if ((uint64_t)W * n >= (1ull << 31)) {
+        set_error("MSM too large: %u points x %d windows exceeds 2^31 entries", n, W);
+        return ZKR_E_UNSUPPORTED;
+    }
+    if (n == 0) return ZKR_OK;
+    char* d_pts = nullptr;
+    ZKR_CUDA(cudaMalloc(&d_pts, AB * (size_t)n));
+    if (n == n_src) {
+        ZKR_CUDA(cudaMemcpyAsync(d_pts, h_points, AB * (size_t)n, cudaMemcpyHostToDevice, st));
+    } else {
+        std::vector<char> packed(AB * (size_t)n);
+        for (uint32_t k = 0; k < n; k++) memcpy(&packed[AB * k], h_points + AB * idx[k], AB);
+        ZKR_CUDA(cudaMemcpyAsync(d_pts, packed.data(), AB * (size_t)n, cudaMemcpyHostToDevice, st));
+        ZKR_CUDA(cudaStreamSynchronize(st));
+        ZKR_CUDA(cudaMalloc(&b->src_index, 4 * (size_t)n));
+        ZKR_CUDA(cudaMemcpyAsync(b->src_index, idx.data(), 4 * (size_t)n, cudaMemcpyHostToDevice, st));
+        ZKR_CUDA(cudaStreamSynchronize(st));
+        b->bytes += 4 * (size_t)n;
+    }
+    const size_t tbytes = AB * (size_t)n * W;
+    ZKR_CUDA(cudaMalloc(&b->table, tbytes));
+    b->bytes += tbytes;
+    ZKR_LAUNCH(ctx, (k_precompute<F>), ceil_div(n, 64), 64, 0, st, d_pts, b->table, n, b->plan.c, W);
+    ZKR_CUDA(cudaStreamSynchronize(st));
+    ZKR_CUDA(cudaFree(d_pts));
+
+    // work buffers
+    MsmWork& wk = b->work;
+    const size_t total = (size_t)W * n;
+    b->logL = total >= (1u << 22) ? 5 : (total >= (1u << 16) ? 4 : 3);
+    const size_t L = (size_t)1 << b->logL;
+    const size_t T1 = (total + L - 1) / L;
+    b->T1p = (uint32_t)(((T1 + kAccumThreads - 1) / kAccumThreads) * kAccumThreads);
+    for (int i = 0; i < 2; i++) {
+        ZKR_CUDA(cudaMalloc(&wk.keys[i], 4 * total));
+        ZKR_CUDA(cudaMalloc(&wk.vals[i], 4 * total));
+        wk.bytes += 8 * total;
+    }
+    cub::DoubleBuffer<uint32_t> dk(wk.keys[0], wk.keys[1]), dv(wk.vals[0], wk.vals[1]);
+    ZKR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, wk.cub_bytes, dk, dv, (int)total, 0, b->plan.c, st));
+    ZKR_CUDA(cudaMalloc(&wk.cub_tmp, wk.cub_bytes ? wk.cub_bytes : 1));
+    ZKR_CUDA(cudaMalloc(&wk.buckets, XB * (size_t)b->plan.nbuckets));
+    const size_t bnd0 = 2 * (size_t)b->T1p;
+    const size_t lvl = (size_t)1 << kLevelLog;
+    const size_t bnd1 = 2 * (((bnd0 + lvl - 1) / lvl + 63) / 64 * 64);
+    ZKR_CUDA(cudaMalloc(&wk.bnd[0], XB * bnd0));
+    ZKR_CUDA(cudaMalloc(&wk.bnd[1], XB * bnd1));
+    ZKR_CUDA(cudaMalloc(&wk.bnd_keys[0], 4 * bnd0));
+    ZKR_CUDA(cudaMalloc(&wk.bnd_keys[1], 4 * bnd1));
+    ZKR_CUDA(cudaMalloc(&wk.red, XB * 3 * kReduceThreads));
+    ZKR_CUDA(cudaMalloc(&wk.result, XB));
+    ZKR_CUDA(cudaMalloc(&wk.range_err, sizeof(int)));
+    ZKR_CUDA(cudaMemsetAsync(wk.range_err, 0, sizeof(int), st));
+    wk.bytes += wk.cub_bytes + XB * ((size_t)b->plan.nbuckets + bnd0 + bnd1 + 3 * kReduceThreads + 1) + 4 * (bnd0 + bnd1);
+    b->bytes += wk.bytes;
+    static bool attr_done[2] = {false, false};
+    const int which = sizeof(F) == 32 ? 0 : 1;
+    if (!attr_done[which]) {
+        ZKR_CUDA(cudaFuncSetAttribute(k_reduce_stage1<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(XB * kReduceThreads)));
+        ZKR_CUDA(cudaFuncSetAttribute(k_reduce_stage2<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(XB * kReduceThreads)));
+        ZKR_CUDA(cudaFuncSetAttribute((k_accum_affine<F, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+        ZKR_CUDA(cudaFuncSetAttribute((k_accum_affine<F, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+        attr_done[which] = true;
+    }
+    ZKR_CUDA(cudaStreamSynchronize(st));
+    return ZKR_OK;
+}
+
+template <class F>
+int msm_run(zkr_ctx* ctx, cudaStream_t st, const zkr_bases* b, const uint32_t* d_scalars, XYZZ<F>* d_out) {
+    constexpr size_t XB = 4 * sizeof(F);
+    constexpr bool kPrefetch = sizeof(F) == 32;    // G2 is register-bound; no software prefetch there
+    const uint32_t n = b->n;
+    if (n == 0) {
+        ZKR_CUDA(cudaMemsetAsync(d_out, 0, XB, st));
+        return ZKR_OK;
+    }
+    const MsmWork& wk = b->work;
+    const int c = b->plan.c, W = b->plan.W;
+    const uint32_t nb = b->plan.nbuckets;
+    const uint32_t total = (uint32_t)W * n;
+    ZKR_LAUNCH(ctx, k_digits, ceil_div(n, 128), 128, 0, st, d_scalars, b->src_index, n, c, W, nb, wk.keys[0],
+               wk.vals[0], wk.range_err);
+    cub::DoubleBuffer<uint32_t> dk(wk.keys[0], wk.keys[1]), dv(wk.vals[0], wk.vals[1]);
+    size_t tmp = wk.cub_bytes;
+    ZKR_CUDA(cub::DeviceRadixSort::SortPairs(wk.cub_tmp, tmp, dk, dv, (int)total, 0, c, st));
+    ctx->launches += 4;   // CUB: histogram + onesweep passes (not this library's own kernels, counted as a block)
+    ZKR_CUDA(cudaMemsetAsync(wk.buckets, 0, XB * (size_t)nb, st));
+
+    // level 1
+    const int L = 1 << b->logL;
+    const size_t smem = (size_t)(kAccumThreads / 32) * 2 * 32 * (L + 1) * 4;
+    XYZZ<F>* buckets = (XYZZ<F>*)wk.buckets;
+    ZKR_LAUNCH(ctx, (k_accum_affine<F, kPrefetch>), b->T1p / kAccumThreads, kAccumThreads, smem, st, dk.Current(),
+               dv.Current(), total, b->logL, b->table, buckets, (XYZZ<F>*)wk.bnd[0], wk.bnd_keys[0], nb);
+    // boundary levels
+    size_t cnt = 2 * (size_t)b->T1p;
+    int cur = 0;
+    const size_t lvl = (size_t)1 << kLevelLog;
+    for (;;) {
+        const bool fin = cnt <= lvl;
+        const size_t T = (cnt + lvl - 1) / lvl;
+        const unsigned blocks = (unsigned)((T + 63) / 64);
+        ZKR_LAUNCH(ctx, k_accum_xyzz<F>, blocks, 64, 0, st, wk.bnd_keys[cur], (const XYZZ<F>*)wk.bnd[cur],
+                   (uint32_t)cnt, kLevelLog, buckets, (XYZZ<F>*)wk.bnd[cur ^ 1], wk.bnd_keys[cur ^ 1], nb, fin);
+        if (fin) break;
+        cnt = 2 * (size_t)blocks * 64;
+        cur ^= 1;
+    }
+    // bucket reduction
+    uint32_t G = nb / (kReduceThreads * 16);
+    if (G < 1) G = 1;
+    if (G > 128) G = 128;
+    const uint32_t K = (nb + G * kReduceThreads - 1) / (G * kReduceThreads);
+    ZKR_LAUNCH(ctx, k_reduce_stage1<F>, G, kReduceThreads, XB * kReduceThreads, st, buckets, nb, K, (XYZZ<F>*)wk.red);
+    ZKR_LAUNCH(ctx, k_reduce_stage2<F>, 1, kReduceThreads, XB * kReduceThreads, st, (const XYZZ<F>*)wk.red, G, K, d_out);
+    return ZKR_OK;
+}
+
+}  // namespace zkr

@@ -1,0 +1,487 @@
+// Radix-2^k NTT over BN254 Fr and the H = (A.B - C)/Z pipeline.
+//
+// Replaces websnark fft_ifft / fft_fft / fft_mulN inside calcH of groth16GenProof
+// (/root/reference/operator/src/snarks/common.ts:29) and snarkjs PolField.ifft / mul
+// (prover_groth.js calculateH).  omega_k = 5^((r-1)/2^k) as in snarkjs polfield.js.
+//
+// Structure (DESIGN.md "NTT"):
+//   * N = 2^n is split into <= 3 passes of <= 11 bits (four-step / Bailey).  One pass = one kernel:
+//     a CTA stages a tile of 2^k rows x 2^c adjacent columns (<= 2048 elements, 72 KB) in shared
+//     memory with coalesced 128-bit loads, runs the 2^k-point sub-NTT in radix-8 register stages
+//     (each thread owns 8 elements = 3 butterfly levels between two __syncthreads), applies the
+//     inter-pass twiddle omega_N'^(col * rev(row)) in registers, and streams the tile back.
+//   * shared memory is limb-major (8 planes of u32) with a 1-in-8 pad so every register-stage
+//     access pattern is bank-conflict free (or 2-way at worst).
+//   * DIF (natural in, bit-reversed out) and its transpose DIT (bit-reversed in, natural out) share
+//     the kernel; the prover chains DIF^-1 -> DIT -> DIF^-1 so no bit-reversal pass is ever run.
+//   * data may be in standard OR Montgomery form: every constant (twiddles, scalings) is stored in
+//     Montgomery form and mont_mul(x, cR) = x*c keeps the form of x.
+#include "common.cuh"
+#include "fp.cuh"
+
+namespace zkr {
+
+constexpr int kTileLog = 11;
+
+struct NttRoots {
+    Fr w, wi;        // omega_N, omega_N^-1
+    Fr g, gi;        // omega_2N (coset shift), inverse
+    Fr ninv;         // 1/N
+    Fr hconst;       // R/(2N): mont_mul(x/R, .) = x/(2N)   (H pipeline final scaling)
+    Fr one;
+};
+
+struct NttTables {
+    int log_n = 0, kw = 0, lb = 0;
+    NttRoots* roots = nullptr;
+    Fr *wsub_f = nullptr, *wsub_i = nullptr;                              // omega_{2^kw}^{+-j}, j < 2^(kw-1)
+    Fr *tw_lo_f = nullptr, *tw_hi_f = nullptr, *tw_lo_i = nullptr, *tw_hi_i = nullptr;  // omega_N^{+-X}
+    Fr *cs_lo = nullptr, *cs_hi = nullptr, *cs_hi_n = nullptr;            // g^j ; hi / hi * 1/N
+    Fr *ci_lo = nullptr, *ci_hi_n = nullptr, *ci_hi_h = nullptr;          // g^-j ; hi * 1/N ; hi * R/(2N)
+    size_t bytes = 0;
+};
+
+namespace {
+
+__device__ __forceinline__ Fr fr_const(const uint32_t (&l)[8]) {
+    Fr r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = l[i];
+    return r;
+}
+
+__device__ Fr fr_pow(Fr base, unsigned long long e) {
+    Fr acc = Fr::one();
+    while (e) {
+        if (e & 1) acc = acc * base;
+        base = base.sqr();
+        e >>= 1;
+    }
+    return acc;
+}
+
+__global__ void k_ntt_roots(NttRoots* out, int log_n) {
+    // omega_28 = 5^((r-1)/2^28), Montgomery form (KAT: SURVEY.md B.1)
+    const uint32_t W28[8] = {0x80d13d9cu, 0x636e7355u, 0x2445ffd6u, 0xa22bf374u,
+                             0x1eb203d8u, 0x56452ac0u, 0x2963f9e7u, 0x1860ef94u};
+    const uint32_t INV2[8] = {0x1ffffffeu, 0x783c14d8u, 0x0c8d1eddu, 0xaf982f6fu,
+                              0xfcfd4f45u, 0x8f5f7492u, 0x3d9cbfacu, 0x1f37631au};
+    Fr g = fr_const(W28);
+    for (int i = 28; i > log_n + 1; i--) g = g.sqr();
+    Fr w = g.sqr();
+    Fr nn = Fr::zero();
+    nn.v[0] = 1u << log_n;
+    nn = nn.to_mont();
+    NttRoots r;
+    r.w = w;
+    r.wi = w.inverse();
+    r.g = g;
+    r.gi = g.inverse();
+    r.ninv = nn.inverse();
+    r.hconst = Fr::r2() * r.ninv * fr_const(INV2);   // Montgomery form of R/(2N)
+    r.one = Fr::one();
+    *out = r;
+}
+
+// out[i] = cst * base^(i * stride)
+__global__ void k_pow_table(Fr* out, unsigned count, const Fr* base, unsigned long long stride, const Fr* cst) {
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    Fr v = fr_pow(*base, (unsigned long long)i * stride);
+    if (cst) v = v * *cst;
+    v.store(out + i);
+}
+
+__device__ __forceinline__ int slot_of(int e) { return e + (e >> 3); }
+
+template <bool DIT>
+__global__ void __launch_bounds__(256)
+k_ntt_pass(Fr* __restrict__ data, int k, int c, int s, int chunk_log, const Fr* __restrict__ W, int kw,
+           const Fr* __restrict__ tlo, const Fr* __restrict__ thi, int lb, int tw_shift) {
+    extern __shared__ uint32_t sm[];
+    const int T = k + c;
+    const int tile = 1 << T;
+    const int plane = tile + (tile >> 3) + 4;
+    const int tid = threadIdx.x;
+    const unsigned cgmask = (1u << (s - c)) - 1;
+    const unsigned cg = blockIdx.x & cgmask;
+    const size_t q = blockIdx.x >> (s - c);
+    Fr* chunk = data + (q << chunk_log);
+    const unsigned c0 = cg << c;
+    const int cmask = (1 << c) - 1;
+
+    // ---- global -> shared, 16-byte units
+    for (int u = tid; u < 2 * tile; u += blockDim.x) {
+        int e = u >> 1, half = u & 1;
+        int row = e >> c, col = e & cmask;
+        const uint4* src = reinterpret_cast<const uint4*>(chunk + ((size_t)row << s) + c0 + col) + half;
+        uint4 v = *src;
+        uint32_t* d = sm + (4 * half) * plane + slot_of(e);
+        d[0] = v.x;
+        d[plane] = v.y;
+        d[2 * plane] = v.z;
+        d[3 * plane] = v.w;
+    }
+    __syncthreads();
+
+    const unsigned lbmask = (1u << lb) - 1;
+    int bit = DIT ? c : T - 1;
+    bool first = true;
+    while (DIT ? (bit <= T - 1) : (bit >= c)) {
+        int lo, act_lo, act_hi;
+        if (DIT) {
+            lo = bit > T - 3 ? T - 3 : bit;
+            act_lo = bit;
+            act_hi = lo + 2;
+        } else {
+            lo = bit < 2 ? 0 : bit - 2;
+            act_hi = bit;
+            act_lo = lo > c ? lo : c;
+        }
+        const int base = ((tid >> lo) << (lo + 3)) | (tid & ((1 << lo) - 1));
+        Fr x[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const uint32_t* p = sm + slot_of(base + (j << lo));
+#pragma unroll
+            for (int l = 0; l < 8; l++) x[j].v[l] = p[l * plane];
+        }
+        const bool tw_now = (s > 0) && (DIT ? first : (act_lo == c));
+        if (DIT && tw_now) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                int e = base + (j << lo);
+                unsigned rho = e >> c, col = e & cmask;
+                unsigned rev = __brev(rho) >> (32 - k);
+                unsigned X = ((c0 + col) * rev) << tw_shift;
+                Fr t = Fr::load_ro(tlo + (X & lbmask)) * Fr::load_ro(thi + (X >> lb));
+                x[j] = x[j] * t;
+            }
+        }
+#pragma unroll
+        for (int ii = 0; ii < 3; ii++) {
+            const int i = DIT ? ii : 2 - ii;
+            const int p = lo + i;
+            if (p < act_lo || p > act_hi) continue;
+            const int pc = p - c;                  // butterfly half-size = 2^pc rows
+#pragma unroll
+            for (int jl = 0; jl < (1 << i); jl++) {
+                Fr w;
+                if (pc > 0) {
+                    unsigned rowbits = ((unsigned)(base | (jl << lo)) >> c) & ((1u << pc) - 1);
+                    w = Fr::load_ro(W + ((size_t)rowbits << (kw - 1 - pc)));
+                }
+#pragma unroll
+                for (int ju = 0; ju < (1 << (2 - i)); ju++) {
+                    const int j0 = jl | (ju << (i + 1));
+                    const int j1 = j0 | (1 << i);
+                    if (DIT) {
+                        Fr v = pc > 0 ? x[j1] * w : x[j1];
+                        Fr u = x[j0];
+                        x[j0] = u + v;
+                        x[j1] = u - v;
+                    } else {
+                        Fr u = x[j0], v = x[j1];
+                        x[j0] = u + v;
+                        Fr d = u - v;
+                        x[j1] = pc > 0 ? d * w : d;
+                    }
+                }
+            }
+        }
+        if (!DIT && tw_now) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                int e = base + (j << lo);
+                unsigned rho = e >> c, col = e & cmask;
+                unsigned rev = __brev(rho) >> (32 - k);
+                unsigned X = ((c0 + col) * rev) << tw_shift;
+                Fr t = Fr::load_ro(tlo + (X & lbmask)) * Fr::load_ro(thi + (X >> lb));
+                x[j] = x[j] * t;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            uint32_t* p = sm + slot_of(base + (j << lo));
+#pragma unroll
+            for (int l = 0; l < 8; l++) p[l * plane] = x[j].v[l];
+        }
+        __syncthreads();
+        first = false;
+        bit = DIT ? act_hi + 1 : act_lo - 1;
+    }
+
+    // ---- shared -> global
+    for (int u = tid; u < 2 * tile; u += blockDim.x) {
+        int e = u >> 1, half = u & 1;
+        int row = e >> c, col = e & cmask;
+        const uint32_t* d = sm + (4 * half) * plane + slot_of(e);
+        uint4 v = make_uint4(d[0], d[plane], d[2 * plane], d[3 * plane]);
+        uint4* dst = reinterpret_cast<uint4*>(chunk + ((size_t)row << s) + c0 + col) + half;
+        *dst = v;
+    }
+}
+
+// N = 2 or 4: one thread, direct DFT
+__global__ void k_ntt_tiny(Fr* data, int log_n, const Fr* root, bool bitrev_in, bool bitrev_out) {
+    int n = 1 << log_n;
+    Fr x[4], y[4];
+    for (int i = 0; i < n; i++) {
+        int pos = bitrev_in ? (int)(__brev(i) >> (32 - log_n)) : i;
+        x[i] = Fr::load(data + pos);
+    }
+    Fr w = *root;
+    for (int kk = 0; kk < n; kk++) {
+        Fr acc = Fr::zero();
+        Fr wk = fr_pow(w, kk), t = Fr::one();
+        for (int i = 0; i < n; i++) {
+            acc = acc + x[i] * t;
+            t = t * wk;
+        }
+        y[kk] = acc;
+    }
+    for (int kk = 0; kk < n; kk++) {
+        int pos = bitrev_out ? (int)(__brev(kk) >> (32 - log_n)) : kk;
+        y[kk].store(data + pos);
+    }
+}
+
+__global__ void k_pointwise_mul(Fr* out, const Fr* a, const Fr* b, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    (Fr::load(a + i) * Fr::load(b + i)).store(out + i);
+}
+
+// x[p] *= lo[j & mask] * hi[j >> lb],  j = bitrev(p) or p
+__global__ void k_scale_pow(Fr* x, size_t n, int log_n, const Fr* lo, const Fr* hi, int lb, bool bitrev_idx) {
+    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    unsigned j = bitrev_idx ? (__brev((unsigned)p) >> (32 - log_n)) : (unsigned)p;
+    Fr t = Fr::load_ro(lo + (j & ((1u << lb) - 1))) * Fr::load_ro(hi + (j >> lb));
+    (Fr::load(x + p) * t).store(x + p);
+}
+
+__global__ void k_scale_const(Fr* x, size_t n, const Fr* cst) {
+    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    (Fr::load(x + p) * *cst).store(x + p);
+}
+
+// out[bitrev(p)] = x[p] * cst * (lo/hi power of j = bitrev(p), if lo != null)
+__global__ void k_bitrev_scale(Fr* out, const Fr* x, size_t n, int log_n, const Fr* cst, const Fr* lo,
+                               const Fr* hi, int lb) {
+    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    unsigned j = __brev((unsigned)p) >> (32 - log_n);
+    Fr v = Fr::load(x + p);
+    if (lo) v = v * (Fr::load_ro(lo + (j & ((1u << lb) - 1))) * Fr::load_ro(hi + (j >> lb)));
+    else if (cst) v = v * *cst;
+    v.store(out + j);
+}
+
+// h[p or bitrev(p)] = S[p] * K - P[p] * (gi^j * K),  j = bitrev(p), K = R/(2N)  (see h_pipeline)
+__global__ void k_h_final(Fr* h, const Fr* S, const Fr* P, size_t n, int log_n, const Fr* kconst,
+                          const Fr* lo, const Fr* hi, int lb, bool bitrev_out) {
+    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    unsigned j = __brev((unsigned)p) >> (32 - log_n);
+    Fr t = Fr::load_ro(lo + (j & ((1u << lb) - 1))) * Fr::load_ro(hi + (j >> lb));
+    Fr v = Fr::load(S + p) * *kconst - Fr::load(P + p) * t;
+    v.store(h + (bitrev_out ? p : (size_t)j));
+}
+
+int plan_passes(int n, int* ks) {
+    int np = (n + kTileLog - 1) / kTileLog;
+    if (np < 1) np = 1;
+    int base = n / np, rem = n % np;
+    for (int i = 0; i < np; i++) ks[i] = base + (i < rem ? 1 : 0);
+    return np;
+}
+
+}  // namespace
+
+void ntt_tables_free(NttTables* t) {
+    if (!t) return;
+    Fr** ps[] = {&t->wsub_f, &t->wsub_i, &t->tw_lo_f, &t->tw_hi_f, &t->tw_lo_i, &t->tw_hi_i, &t->cs_lo,
+                 &t->cs_hi, &t->cs_hi_n, &t->ci_lo, &t->ci_hi_n, &t->ci_hi_h};
+    for (Fr** p : ps) cudaFree(*p);
+    cudaFree(t->roots);
+    delete t;
+}
+
+static int pow_table(zkr_ctx* ctx, cudaStream_t st, Fr** out, unsigned count, const Fr* base,
+                     unsigned long long stride, const Fr* cst, size_t* bytes) {
+    ZKR_CUDA(cudaMalloc(out, (size_t)count * sizeof(Fr)));
+    *bytes += (size_t)count * sizeof(Fr);
+    ZKR_LAUNCH(ctx, k_pow_table, ceil_div(count, 128), 128, 0, st, *out, count, base, stride, cst);
+    return ZKR_OK;
+}
+
+int ntt_get_tables(zkr_ctx* ctx, int log_n, NttTables** out) {
+    auto it = ctx->ntt.find(log_n);
+    if (it != ctx->ntt.end()) {
+        *out = it->second;
+        return ZKR_OK;
+    }
+    if (log_n < 1 || log_n > 27) {
+        set_error("NTT size 2^%d unsupported (1..27)", log_n);
+        return ZKR_E_UNSUPPORTED;
+    }
+    static bool attr_done = false;
+    if (!attr_done) {
+        ZKR_CUDA(cudaFuncSetAttribute(k_ntt_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        ZKR_CUDA(cudaFuncSetAttribute(k_ntt_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        attr_done = true;
+    }
+    NttTables* t = new NttTables();
+    t->log_n = log_n;
+    t->kw = log_n < kTileLog ? log_n : kTileLog;
+    t->lb = (log_n + 1) / 2;
+    cudaStream_t st = ctx->s[0];
+    ZKR_CUDA(cudaMalloc(&t->roots, sizeof(NttRoots)));
+    ZKR_LAUNCH(ctx, k_ntt_roots, 1, 1, 0, st, t->roots, log_n);
+    const unsigned nlo = 1u << t->lb, nhi = 1u << (log_n - t->lb);
+    const unsigned long long hs = 1ull << t->lb;
+    NttRoots* r = t->roots;
+    const unsigned nsub = 1u << (t->kw - 1);
+    const unsigned long long sub_stride = 1ull << (log_n - t->kw);
+    ZKR_TRY(pow_table(ctx, st, &t->wsub_f, nsub, &r->w, sub_stride, nullptr, &t->bytes));
+    ZKR_TRY(pow_table(ctx, st, &t->wsub_i, nsub, &r->wi, sub_stride, nullptr, &t->bytes));
+    ZKR_TRY(pow_table(ctx, st, &t->tw_lo_f, nlo, &r->w, 1, nullptr, &t->bytes));
+    ZKR_TRY(pow_table(ctx, st, &t->tw_hi_f, nhi, &r->w, hs, nullptr, &t->bytes));
+    ZKR_TRY(pow_table(ctx, st, &t->tw_lo_i, nlo, &r->wi, 1, nullptr, &t->bytes));
+    ZKR_TRY(pow_table(ctx, st, &t->tw_hi_i, nhi, &r->wi, hs, nullptr, &t->bytes));
+    ZKR_TRY(pow_table(ctx, st, &t->cs_lo, nlo, &r->g, 1, nullptr, &t->bytes));
+    ZKR_TRY(pow_table(ctx, st, &t->cs_hi, nhi, &r->g, hs, nullptr, &t->bytes));
+    ZKR_TRY(pow_table(ctx, st, &t->cs_hi_n, nhi, &r->g, hs, &r->ninv, &t->bytes));
+    ZKR_TRY(pow_table(ctx, st, &t->ci_lo, nlo, &r->gi, 1, nullptr, &t->bytes));
+    ZKR_TRY(pow_table(ctx, st, &t->ci_hi_n, nhi, &r->gi, hs, &r->ninv, &t->bytes));
+    ZKR_TRY(pow_table(ctx, st, &t->ci_hi_h, nhi, &r->gi, hs, &r->hconst, &t->bytes));
+    ZKR_CUDA(cudaStreamSynchronize(st));
+    ctx->ntt[log_n] = t;
+    *out = t;
+    return ZKR_OK;
+}
+
+// In-place transform of 2^log_n elements on `st`.
+//   dit == false: natural in  -> bit-reversed out (DIF)
+//   dit == true : bit-reversed in -> natural out  (DIT)
+// inverse selects omega^-1; no 1/N scaling is applied here.
+int ntt_run(zkr_ctx* ctx, cudaStream_t st, Fr* data, int log_n, bool dit, bool inverse) {
+    NttTables* t;
+    ZKR_TRY(ntt_get_tables(ctx, log_n, &t));
+    if (log_n < 3) {
+        ZKR_LAUNCH(ctx, k_ntt_tiny, 1, 1, 0, st, data, log_n, inverse ? &t->roots->wi : &t->roots->w, dit, !dit);
+        return ZKR_OK;
+    }
+    int ks[4];
+    const int np = plan_passes(log_n, ks);
+    const Fr* W = inverse ? t->wsub_i : t->wsub_f;
+    const Fr* tlo = inverse ? t->tw_lo_i : t->tw_lo_f;
+    const Fr* thi = inverse ? t->tw_hi_i : t->tw_hi_f;
+    for (int step = 0; step < np; step++) {
+        const int i = dit ? np - 1 - step : step;
+        int chunk_log = log_n;
+        for (int j = 0; j < i; j++) chunk_log -= ks[j];
+        const int k = ks[i];
+        const int s = chunk_log - k;
+        int c = kTileLog - k;
+        if (c > s) c = s;
+        const int T = k + c;
+        const int tile = 1 << T;
+        const int threads = tile / 8;
+        const size_t smem = (size_t)8 * (tile + (tile >> 3) + 4) * sizeof(uint32_t);
+        const unsigned blocks = 1u << (log_n - T);
+        // sub-NTT root: omega_{2^k} = W-table stride 2^(kw-k); the table is indexed in units of omega_{2^kw}
+        if (dit) ZKR_LAUNCH(ctx, k_ntt_pass<true>, blocks, threads, smem, st, data, k, c, s, chunk_log, W, t->kw,
+                            tlo, thi, t->lb, log_n - chunk_log);
+        else ZKR_LAUNCH(ctx, k_ntt_pass<false>, blocks, threads, smem, st, data, k, c, s, chunk_log, W, t->kw,
+                        tlo, thi, t->lb, log_n - chunk_log);
+    }
+    return ZKR_OK;
+}
+
+// h = U where A*B = L + x^m U  (SURVEY.md B.4 method iv; oracle: calc_h_lu).
+//   S = A_T . B_T            -> DIF^-1 -> m (L+U)_j           at bit-reversed positions
+//   a, b = DIF^-1(A_T, B_T)  -> * g^j/m -> DIT -> A, B on the coset g<omega>  (natural order)
+//   P = A . B                -> DIF^-1 -> m (L-U)_j g^j
+//   h_j = ((L+U)_j - (L-U)_j) / 2
+// Pointwise products of two data vectors pick up a factor 1/R (Montgomery); the final constants
+// carry R/(2m) so the output has the same form (standard or Montgomery) as the inputs.
+int h_pipeline(zkr_ctx* ctx, cudaStream_t st, Fr* A, Fr* B, Fr* S, Fr* h, int log_m, bool bitrev_out) {
+    NttTables* t;
+    ZKR_TRY(ntt_get_tables(ctx, log_m, &t));
+    const size_t m = (size_t)1 << log_m;
+    const int blk = 128, grid = ceil_div(m, blk);
+    ZKR_LAUNCH(ctx, k_pointwise_mul, grid, blk, 0, st, S, A, B, m);
+    ZKR_TRY(ntt_run(ctx, st, A, log_m, false, true));
+    ZKR_TRY(ntt_run(ctx, st, B, log_m, false, true));
+    ZKR_TRY(ntt_run(ctx, st, S, log_m, false, true));
+    ZKR_LAUNCH(ctx, k_scale_pow, grid, blk, 0, st, A, m, log_m, t->cs_lo, t->cs_hi_n, t->lb, true);
+    ZKR_LAUNCH(ctx, k_scale_pow, grid, blk, 0, st, B, m, log_m, t->cs_lo, t->cs_hi_n, t->lb, true);
+    ZKR_TRY(ntt_run(ctx, st, A, log_m, true, false));
+    ZKR_TRY(ntt_run(ctx, st, B, log_m, true, false));
+    ZKR_LAUNCH(ctx, k_pointwise_mul, grid, blk, 0, st, A, A, B, m);
+    ZKR_TRY(ntt_run(ctx, st, A, log_m, false, true));
+    ZKR_LAUNCH(ctx, k_h_final, grid, blk, 0, st, h, S, A, m, log_m, &t->roots->hconst, t->ci_lo, t->ci_hi_h,
+               t->lb, bitrev_out);
+    return ZKR_OK;
+}
+
+}  // namespace zkr
+
+using namespace zkr;
+
+extern "C" int zkr_ntt(zkr_ctx* ctx, void* data, int log_n, int mode, int on_device) {
+    if (!ctx || !data || log_n < 1) return ZKR_E_INVALID;
+    const int base_mode = mode & 0xf;
+    const bool br_out = mode & ZKR_NTT_BITREV_OUT, br_in = mode & ZKR_NTT_BITREV_IN;
+    if (base_mode > 3 || (br_out && br_in)) return ZKR_E_INVALID;
+    DeviceGuard g(ctx->device);
+    NttTables* t;
+    ZKR_TRY(ntt_get_tables(ctx, log_n, &t));
+    const size_t n = (size_t)1 << log_n, bytes = n * sizeof(Fr);
+    cudaStream_t st = ctx->user_stream;
+    Fr* d = (Fr*)data;
+    if (!on_device) {
+        void* p;
+        ZKR_TRY(ctx->scratch_get("ntt_io", bytes, &p));
+        d = (Fr*)p;
+        ZKR_CUDA(cudaMemcpyAsync(d, data, bytes, cudaMemcpyHostToDevice, st));
+    }
+    const bool inverse = base_mode == ZKR_NTT_INVERSE || base_mode == ZKR_NTT_COSET_INVERSE;
+    const bool coset = base_mode >= ZKR_NTT_COSET_FORWARD;
+    const int blk = 128, grid = ceil_div(n, blk);
+    if (coset && !inverse)   // x_j *= g^j, j = natural coefficient index
+        ZKR_LAUNCH(ctx, k_scale_pow, grid, blk, 0, st, d, n, log_n, t->cs_lo, t->cs_hi, t->lb, br_in);
+    ZKR_TRY(ntt_run(ctx, st, d, log_n, br_in, inverse));
+    const bool out_is_bitrev = !br_in;   // DIF leaves bit-reversed order
+    if (br_out || br_in) {
+        // stay in the order the transform produced; apply the inverse scalings in place
+        if (inverse && coset)
+            ZKR_LAUNCH(ctx, k_scale_pow, grid, blk, 0, st, d, n, log_n, t->ci_lo, t->ci_hi_n, t->lb, out_is_bitrev);
+        else if (inverse)
+            ZKR_LAUNCH(ctx, k_scale_const, grid, blk, 0, st, d, n, &t->roots->ninv);
+    } else {
+        void* p;
+        ZKR_TRY(ctx->scratch_get("ntt_tmp", bytes, &p));
+        Fr* tmp = (Fr*)p;
+        const Fr* cst = inverse && !coset ? &t->roots->ninv : nullptr;
+        const Fr* lo = inverse && coset ? t->ci_lo : nullptr;
+        ZKR_LAUNCH(ctx, k_bitrev_scale, grid, blk, 0, st, tmp, d, n, log_n, cst, lo, t->ci_hi_n, t->lb);
+        ZKR_CUDA(cudaMemcpyAsync(d, tmp, bytes, cudaMemcpyDeviceToDevice, st));
+    }
+    if (!on_device) {
+        ZKR_CUDA(cudaMemcpyAsync(data, d, bytes, cudaMemcpyDeviceToHost, st));
+        ZKR_CUDA(cudaStreamSynchronize(st));
+    }
+    return ZKR_OK;
+}
+
+extern "C" int zkr_h_from_evals_dev(zkr_ctx* ctx, void* d_a_t, void* d_b_t, int log_m, void* d_h_out, int bitrev_out) {
+    if (!ctx || !d_a_t || !d_b_t || !d_h_out || log_m < 1) return ZKR_E_INVALID;
+    DeviceGuard g(ctx->device);
+    void* p;
+    ZKR_TRY(ctx->scratch_get("h_S", ((size_t)1 << log_m) * sizeof(Fr), &p));
+    return h_pipeline(ctx, ctx->user_stream, (Fr*)d_a_t, (Fr*)d_b_t, (Fr*)p, (Fr*)d_h_out, log_m, bitrev_out != 0);
+}

@@ -1,0 +1,103 @@
+"""GPU parity: NTT / coset NTT / H pipeline over Fr vs the recursive radix-2 oracle, bit-exact."""
+import ctypes as C
+import random
+
+import numpy as np
+import pytest
+
+from oracle import groth16 as g
+from oracle.bn254 import R
+from simple_zk_rollups_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+FWD, INV, CFWD, CINV = 0, 1, 2, 3
+BR_OUT, BR_IN = 0x10, 0x20
+
+
+def pack(vals):
+    return np.frombuffer(b"".join(int(v).to_bytes(32, "little") for v in vals), dtype=np.uint8).copy()
+
+
+def unpack(arr):
+    b = arr.tobytes()
+    return [int.from_bytes(b[i:i + 32], "little") for i in range(0, len(b), 32)]
+
+
+def brev(x, bits):
+    return [x[g.bit_reverse(i, bits)] for i in range(len(x))]
+
+
+def run(zctx, vals, log_n, mode):
+    buf = pack(vals)
+    _lib.check(_lib.lib().zkr_ntt(zctx, _lib.buf_ptr(buf), log_n, mode, 0))
+    return unpack(buf)
+
+
+@pytest.mark.parametrize("log_n", [1, 2, 3, 4, 5, 6, 8, 10, 11, 12, 13, 14, 16])
+def test_ntt_modes(zctx, log_n):
+    rng = random.Random(log_n)
+    n = 1 << log_n
+    x = [rng.randrange(R) for _ in range(n)]
+    x[0] = R - 1
+    if n > 2:
+        x[1] = 0
+    shift = g.root_of_unity(log_n + 1)
+    want = {FWD: g.ntt(x), INV: g.ntt(x, inverse=True), CFWD: g.coset_ntt(x, shift), CINV: g.coset_intt(x, shift)}
+    for mode, w in want.items():
+        assert run(zctx, x, log_n, mode) == w, "mode %d" % mode
+        assert run(zctx, x, log_n, mode | BR_OUT) == brev(w, log_n), "mode %d bitrev out" % mode
+        assert run(zctx, brev(x, log_n), log_n, mode | BR_IN) == w, "mode %d bitrev in" % mode
+
+
+def test_ntt_roundtrip_large(zctx):
+    """size-independent property at 2^20 / 2^22: iNTT(NTT(x)) == x and evaluation at one point."""
+    L = _lib.lib()
+    for log_n in (20, 22):
+        n = 1 << log_n
+        rs = np.random.RandomState(log_n)
+        buf = rs.randint(0, 256, size=n * 32, dtype=np.uint8)
+        buf.reshape(n, 32)[:, 31] &= 0x1F          # < 2^253 < r
+        orig = buf.copy()
+        _lib.check(L.zkr_ntt(zctx, _lib.buf_ptr(buf), log_n, FWD, 0))
+        ev = buf.copy()
+        _lib.check(L.zkr_ntt(zctx, _lib.buf_ptr(buf), log_n, INV, 0))
+        assert np.array_equal(buf, orig)
+        # Horner check of evaluation index k: X[k] = sum x_j w^(jk), for a sparse probe instead:
+        # linearity probe -- NTT(e_5) has X[k] = w^(5k)
+        probe = np.zeros(n * 32, dtype=np.uint8)
+        probe[5 * 32] = 1
+        _lib.check(L.zkr_ntt(zctx, _lib.buf_ptr(probe), log_n, FWD, 0))
+        w = g.root_of_unity(log_n)
+        for k in (0, 1, 2, 12345, n - 1):
+            got = int.from_bytes(probe[k * 32:(k + 1) * 32].tobytes(), "little")
+            assert got == pow(w, 5 * k, R)
+        del ev
+
+
+@pytest.mark.parametrize("log_m", [2, 3, 6, 10, 12, 13])
+def test_h_pipeline(zctx, log_m):
+    """h from A_T, B_T evaluations == oracle calc_h_lu / calc_h_websnark on the same vectors."""
+    L = _lib.lib()
+    rng = random.Random(100 + log_m)
+    m = 1 << log_m
+    at = [rng.randrange(R) for _ in range(m)]
+    bt = [rng.randrange(R) for _ in range(m)]
+    pk = dict(domainSize=m, polsA=[{i: at[i] for i in range(m)}], polsB=[{i: bt[i] for i in range(m)}])
+    want = g.calc_h_lu(pk, [1])
+    if log_m <= 10:
+        assert want == g.calc_h_websnark(pk, [1])
+    da, db, dh = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    for d in (da, db, dh):
+        _lib.check(L.zkr_dev_malloc(zctx, m * 32, C.byref(d)))
+    for bitrev in (0, 1):
+        A, B = pack(at), pack(bt)
+        _lib.check(L.zkr_dev_upload(zctx, da, _lib.buf_ptr(A), m * 32))
+        _lib.check(L.zkr_dev_upload(zctx, db, _lib.buf_ptr(B), m * 32))
+        _lib.check(L.zkr_h_from_evals_dev(zctx, da, db, log_m, dh, bitrev))
+        out = np.zeros(m * 32, dtype=np.uint8)
+        _lib.check(L.zkr_dev_download(zctx, _lib.buf_ptr(out), dh, m * 32))
+        got = unpack(out)
+        assert got == (brev(want, log_m) if bitrev else want)
+    for d in (da, db, dh):
+        _lib.check(L.zkr_dev_free(zctx, d))
