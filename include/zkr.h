@@ -178,6 +178,9 @@ int zkr_test_field_op(zkr_ctx* ctx, int field, int op, const void* a, const void
  * 3 = xyzz full add of (P+P) and Q (exercises add()).  Points: affine Montgomery, x == 0 = infinity;
  * out affine Montgomery. */
 int zkr_test_curve_op(zkr_ctx* ctx, int group, int op, const void* p, const void* q_or_k, void* out, size_t n);
+/* white-box: copy an internal MSM work buffer of `b` to the host (what: 0 table, 1/2 keys, 3/4 vals,
+ * 5 buckets, 6 result, 7 reduce partials, 8/9 boundary keys, 10/11 boundary partials). */
+int zkr_test_bases_peek(const zkr_bases* b, int what, size_t offset, void* out, size_t bytes);
 /* integer-pipe microbenchmarks: which: 0 = IMAD chain, 1 = IMAD.WIDE chain, 2 = Fq modmul chain,
  * 3 = XYZZ mixed-add chain.  Returns operations per second (IMADs / modmuls / madds) in *ops_per_s. */
 int zkr_microbench(zkr_ctx* ctx, int which, int iters, double* ops_per_s, float* ms);

@@ -67,6 +67,8 @@ extern "C" int zkr_ctx_create(int device, zkr_ctx** out) {
         return ZKR_E_NO_DEVICE;
     }
     DeviceGuard g(device);
+    // Out-of-line G2 helpers nest 256-byte by-value frames; give every thread a generous stack.
+    ZKR_CUDA(cudaDeviceSetLimit(cudaLimitStackSize, 16 * 1024));
     zkr_ctx* c = new zkr_ctx();
     c->device = device;
     c->sm_count = prop.multiProcessorCount;

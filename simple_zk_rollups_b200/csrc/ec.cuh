@@ -127,7 +127,7 @@ struct XYZZ {
     }
 
     // affine, Montgomery form; identity -> (0, 0)
-    __device__ Affine<F> to_affine() const {
+    __device__ __forceinline__ Affine<F> to_affine() const {
         if (is_inf()) return {F::zero(), F::zero()};
         // 1/zzz gives both: 1/zz = (1/zzz)^2 * zz^2 ... cheaper: one inversion of zzz, then
         // 1/zz = zzz^-2 * zz^2  (since zz^3 = zzz^2  =>  zz^-1 = zz^2 * zzz^-2)
@@ -142,14 +142,31 @@ using G2Affine = Affine<Fq2>;
 using G1XYZZ = XYZZ<Fq>;
 using G2XYZZ = XYZZ<Fq2>;
 
-// k * p, k a 256-bit standard-form integer (LSB-first double-and-add); O(1) uses per proof only
+// Out-of-line helpers for cold paths (block-level bucket reduction).  They are strictly
+// MEMORY-TO-MEMORY: every pointer must address shared or global memory and all big values live
+// inside the callee.  Passing 256-byte structs across a device call boundary (by value, or as
+// pointers to the caller's locals) produced wrong results with nvcc/ptxas 12.9 on sm_100a -- see
+// DESIGN.md "toolchain notes" and tools/scratch/variants.cu for the reproducer.
 template <class F>
-__device__ XYZZ<F> scalar_mul(const XYZZ<F>& p, const uint32_t* k) {
+__device__ __noinline__ void xyzz_add_mem(XYZZ<F>* dst, const XYZZ<F>* a, const XYZZ<F>* b) {
+    XYZZ<F> x = *a;
+    x.add(*b);
+    *dst = x;
+}
+template <class F>
+__device__ __noinline__ void xyzz_dbl_mem(XYZZ<F>* dst) {
+    XYZZ<F> x = *dst;
+    *dst = x.dbl();
+}
+
+// k * p, k a 256-bit standard-form integer (LSB-first double-and-add); O(1) uses per proof only.
+template <class F>
+__device__ __forceinline__ XYZZ<F> scalar_mul(XYZZ<F> p, Fr k) {
     XYZZ<F> acc = XYZZ<F>::identity(), base = p;
     int top = 255;
-    while (top >= 0 && !((k[top >> 5] >> (top & 31)) & 1)) top--;
+    while (top >= 0 && !((k.v[top >> 5] >> (top & 31)) & 1)) top--;
     for (int i = 0; i <= top; i++) {
-        if ((k[i >> 5] >> (i & 31)) & 1) acc.add(base);
+        if ((k.v[i >> 5] >> (i & 31)) & 1) acc.add(base);
         if (i < top) base = base.dbl();
     }
     return acc;

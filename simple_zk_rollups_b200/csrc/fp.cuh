@@ -54,6 +54,10 @@ struct FrParams {   // scalar field r (binarify.ts:87)
 };
 
 // ------------------------------------------------------------------ carry-chain building blocks
+// NOTE on constraints: every asm block below is several instructions long and reads inputs after
+// it has started writing outputs, so write-only outputs MUST be early-clobber ("=&r"); with plain
+// "=r" the compiler may give an output the register of a not-yet-consumed input (seen in practice:
+// out-of-line instantiations produced garbage while inlined ones happened to work).
 // acc[0..7] += {x0,x2,x4,x6} * k laid out 64-bit aligned; the carry out is added into *top.
 __device__ __forceinline__ void mad_row_carry(uint32_t* acc, uint32_t& top, uint32_t x0, uint32_t x2,
                                               uint32_t x4, uint32_t x6, uint32_t k) {
@@ -114,8 +118,8 @@ __device__ __forceinline__ void mul_row(uint32_t* acc, uint32_t x0, uint32_t x2,
         "mul.hi.u32 %5, %10, %12;\n\t"
         "mul.lo.u32 %6, %11, %12;\n\t"
         "mul.hi.u32 %7, %11, %12;"
-        : "=r"(acc[0]), "=r"(acc[1]), "=r"(acc[2]), "=r"(acc[3]), "=r"(acc[4]), "=r"(acc[5]),
-          "=r"(acc[6]), "=r"(acc[7])
+        : "=&r"(acc[0]), "=&r"(acc[1]), "=&r"(acc[2]), "=&r"(acc[3]), "=&r"(acc[4]), "=&r"(acc[5]),
+          "=&r"(acc[6]), "=&r"(acc[7])
         : "r"(x0), "r"(x2), "r"(x4), "r"(x6), "r"(k));
 }
 
@@ -146,8 +150,8 @@ __device__ __forceinline__ void final_sub(uint32_t* r) {
         "subc.cc.u32 %6, %15, %23;\n\t"
         "subc.cc.u32 %7, %16, %24;\n\t"
         "subc.u32 %8, 0, 0;"
-        : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]),
-          "=r"(t[7]), "=r"(borrow)
+        : "=&r"(t[0]), "=&r"(t[1]), "=&r"(t[2]), "=&r"(t[3]), "=&r"(t[4]), "=&r"(t[5]), "=&r"(t[6]),
+          "=&r"(t[7]), "=&r"(borrow)
         : "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
           "r"(P::mod(0)), "r"(P::mod(1)), "r"(P::mod(2)), "r"(P::mod(3)), "r"(P::mod(4)),
           "r"(P::mod(5)), "r"(P::mod(6)), "r"(P::mod(7)));
@@ -233,8 +237,8 @@ struct Fp {
             "addc.cc.u32 %5, %13, %21;\n\t"
             "addc.cc.u32 %6, %14, %22;\n\t"
             "addc.u32 %7, %15, %23;"
-            : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]),
-              "=r"(r.v[6]), "=r"(r.v[7])
+            : "=&r"(r.v[0]), "=&r"(r.v[1]), "=&r"(r.v[2]), "=&r"(r.v[3]), "=&r"(r.v[4]), "=&r"(r.v[5]),
+              "=&r"(r.v[6]), "=&r"(r.v[7])
             : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]),
               "r"(a.v[6]), "r"(a.v[7]), "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]),
               "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
@@ -253,8 +257,8 @@ struct Fp {
             "subc.cc.u32 %6, %15, %23;\n\t"
             "subc.cc.u32 %7, %16, %24;\n\t"
             "subc.u32 %8, 0, 0;"
-            : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]),
-              "=r"(r.v[6]), "=r"(r.v[7]), "=r"(borrow)
+            : "=&r"(r.v[0]), "=&r"(r.v[1]), "=&r"(r.v[2]), "=&r"(r.v[3]), "=&r"(r.v[4]), "=&r"(r.v[5]),
+              "=&r"(r.v[6]), "=&r"(r.v[7]), "=&r"(borrow)
             : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]),
               "r"(a.v[6]), "r"(a.v[7]), "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]),
               "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
@@ -285,7 +289,7 @@ struct Fp {
         return *this * o;
     }
     // a^(p-2); ~380 modmuls, used only O(1) times per proof / per setup element
-    __device__ Fp inverse() const {
+    __device__ __forceinline__ Fp inverse() const {
         Fp base = *this, acc = one();
         uint32_t e[8];
 #pragma unroll
@@ -358,7 +362,7 @@ struct Fq2 {
     }
     __device__ __forceinline__ Fq2 neg() const { return {c0.neg(), c1.neg()}; }
     __device__ __forceinline__ Fq2 dbl() const { return {c0.dbl(), c1.dbl()}; }
-    __device__ Fq2 inverse() const {
+    __device__ __forceinline__ Fq2 inverse() const {
         Fq n = (c0.sqr() + c1.sqr()).inverse();
         return {c0 * n, (c1 * n).neg()};
     }

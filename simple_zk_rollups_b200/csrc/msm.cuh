@@ -61,13 +61,15 @@ __global__ void k_precompute(const char* __restrict__ pts, char* __restrict__ ta
     p.store(table + AB * i);
     XYZZ<F> acc = XYZZ<F>::from_affine(p);
     for (int w = 1; w < W; w++) {
+#pragma unroll 1
         for (int d = 0; d < c; d++) acc = acc.dbl();
-        acc.to_affine().store(table + AB * ((size_t)w * n + i));
+        Affine<F> a = acc.to_affine();
+        a.store(table + AB * ((size_t)w * n + i));
     }
 }
 
 // keys[w n + i] = |digit| - 1 (or sentinel for 0), vals[w n + i] = (w n + i) | sign
-__global__ void k_digits(const uint32_t* __restrict__ scalars, const uint32_t* __restrict__ src_index, uint32_t n,
+static __global__ void k_digits(const uint32_t* __restrict__ scalars, const uint32_t* __restrict__ src_index, uint32_t n,
                          int c, int W, uint32_t sentinel, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
                          int* __restrict__ range_err) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -228,55 +230,45 @@ k_accum_xyzz(const uint32_t* __restrict__ in_keys, const XYZZ<F>* __restrict__ i
 }
 
 // ------------------------------------------------------------------------------------------------
-// block-wide helpers on XYZZ points staged in shared memory (blockDim.x == NT, power of two)
+// block-wide helpers on XYZZ points staged in shared memory (blockDim.x == NT, power of two).
+// All point arithmetic goes through the memory-to-memory helpers of ec.cuh.
+// sum of sp[0..NT) -> sp[0]
 template <class F, int NT>
-__device__ __forceinline__ XYZZ<F> block_sum(XYZZ<F>* sp, const XYZZ<F>& mine, int skip_first) {
+__device__ __forceinline__ void block_sum_inplace(XYZZ<F>* sp) {
     const int l = threadIdx.x;
-    sp[l] = (l < skip_first) ? XYZZ<F>::identity() : mine;
     __syncthreads();
     for (int d = NT / 2; d >= 1; d >>= 1) {
-        if (l < d) {
-            XYZZ<F> a = sp[l];
-            a.add(sp[l + d]);
-            sp[l] = a;
-        }
+        if (l < d) xyzz_add_mem(&sp[l], &sp[l], &sp[l + d]);
         __syncthreads();
     }
-    XYZZ<F> r = sp[0];
-    __syncthreads();
-    return r;
 }
 
-// inclusive suffix sums: returns T_l = sum_{l' >= l} v_l'
+// inclusive suffix sums T_l = sum_{l' >= l} v_l' (Hillis-Steele, ping-pong); returns the buffer holding T
 template <class F, int NT>
-__device__ __forceinline__ XYZZ<F> block_suffix_scan(XYZZ<F>* sp, const XYZZ<F>& mine) {
+__device__ __forceinline__ XYZZ<F>* block_suffix_scan(XYZZ<F>* cur, XYZZ<F>* nxt) {
     const int l = threadIdx.x;
-    XYZZ<F> v = mine;
-    sp[l] = v;
     __syncthreads();
     for (int d = 1; d < NT; d <<= 1) {
-        XYZZ<F> o = XYZZ<F>::identity();
-        const bool has = l + d < NT;
-        if (has) o = sp[l + d];
+        if (l + d < NT) xyzz_add_mem(&nxt[l], &cur[l], &cur[l + d]);
+        else nxt[l] = cur[l];
         __syncthreads();
-        if (has) {
-            v.add(o);
-            sp[l] = v;
-        }
-        __syncthreads();
+        XYZZ<F>* t = cur;
+        cur = nxt;
+        nxt = t;
     }
-    return v;
+    return cur;
 }
 
+// *p = k * *p  (p, tmp in shared memory; single thread)
 template <class F>
-__device__ __forceinline__ XYZZ<F> mul_small(XYZZ<F> p, uint32_t k) {
-    XYZZ<F> acc = XYZZ<F>::identity();
+__device__ __forceinline__ void mul_small_mem(XYZZ<F>* p, XYZZ<F>* tmp, uint32_t k) {
+    *tmp = *p;
+    *p = XYZZ<F>::identity();
     while (k) {
-        if (k & 1) acc.add(p);
+        if (k & 1) xyzz_add_mem(p, p, tmp);
         k >>= 1;
-        if (k) p = p.dbl();
+        if (k) xyzz_dbl_mem(tmp);
     }
-    return acc;
 }
 
 constexpr int kReduceThreads = 256;
@@ -287,59 +279,70 @@ template <class F>
 __global__ void __launch_bounds__(kReduceThreads)
 k_reduce_stage1(const XYZZ<F>* __restrict__ buckets, uint32_t nbuckets, uint32_t K, XYZZ<F>* __restrict__ out) {
     extern __shared__ unsigned char smraw[];
-    XYZZ<F>* sp = reinterpret_cast<XYZZ<F>*>(smraw);
-    const uint32_t u = blockIdx.x * kReduceThreads + threadIdx.x;
+    XYZZ<F>* s0 = reinterpret_cast<XYZZ<F>*>(smraw);
+    XYZZ<F>* s1 = s0 + kReduceThreads;
+    const int l = threadIdx.x;
+    const uint32_t u = blockIdx.x * kReduceThreads + l;
     XYZZ<F> run = XYZZ<F>::identity(), acc = XYZZ<F>::identity();
     const uint64_t b0 = (uint64_t)u * K;
+#pragma unroll 1
     for (int b = (int)K - 1; b >= 0; b--) {
         if (b0 + b < nbuckets) {
             run.add(XYZZ<F>::load(buckets + b0 + b));
             acc.add(run);
         }
     }
-    XYZZ<F> X = block_sum<F, kReduceThreads>(sp, acc, 0);
-    XYZZ<F> T = block_suffix_scan<F, kReduceThreads>(sp, run);
+    s0[l] = acc;
+    block_sum_inplace<F, kReduceThreads>(s0);
+    if (l == 0) s0[0].store(out + 3 * blockIdx.x);            // X_g
     __syncthreads();
-    XYZZ<F> Y = block_sum<F, kReduceThreads>(sp, T, 1);      // sum_{l>=1} T_l = sum_l l*S_l
-    if (threadIdx.x == 0) {
-        X.store(out + 3 * blockIdx.x);
-        Y.store(out + 3 * blockIdx.x + 1);
-        T.store(out + 3 * blockIdx.x + 2);                   // T_0 = Z_g
+    s0[l] = run;
+    XYZZ<F>* T = block_suffix_scan<F, kReduceThreads>(s0, s1);
+    if (l == 0) {
+        T[0].store(out + 3 * blockIdx.x + 2);                 // Z_g = T_0
+        T[0] = XYZZ<F>::identity();
     }
+    block_sum_inplace<F, kReduceThreads>(T);                  // sum_{l>=1} T_l = sum_l l*S_l
+    if (l == 0) T[0].store(out + 3 * blockIdx.x + 1);         // Y_g
 }
 
-// stage 2 (one block of G <= 256 threads): total = sum X + K sum Y + 256 K sum_g g Z_g
+// stage 2 (one block): total = sum X + K sum Y + 256 K sum_g g Z_g
 template <class F>
 __global__ void __launch_bounds__(kReduceThreads)
 k_reduce_stage2(const XYZZ<F>* __restrict__ in, uint32_t G, uint32_t K, XYZZ<F>* __restrict__ out) {
     extern __shared__ unsigned char smraw[];
-    XYZZ<F>* sp = reinterpret_cast<XYZZ<F>*>(smraw);
+    XYZZ<F>* s0 = reinterpret_cast<XYZZ<F>*>(smraw);
+    XYZZ<F>* s1 = s0 + kReduceThreads;
+    __shared__ XYZZ<F> res[3];
     const uint32_t g = threadIdx.x;
-    XYZZ<F> X = XYZZ<F>::identity(), Y = X, Z = X;
-    if (g < G) {
-        X = XYZZ<F>::load(in + 3 * g);
-        Y = XYZZ<F>::load(in + 3 * g + 1);
-        Z = XYZZ<F>::load(in + 3 * g + 2);
-    }
-    XYZZ<F> sx = block_sum<F, kReduceThreads>(sp, X, 0);
-    XYZZ<F> sy = block_sum<F, kReduceThreads>(sp, Y, 0);
-    XYZZ<F> tz = block_suffix_scan<F, kReduceThreads>(sp, Z);
+    const XYZZ<F> id = XYZZ<F>::identity();
+    s0[g] = g < G ? XYZZ<F>::load(in + 3 * g) : id;
+    block_sum_inplace<F, kReduceThreads>(s0);
+    if (g == 0) res[0] = s0[0];                               // sum X
     __syncthreads();
-    XYZZ<F> sgz = block_sum<F, kReduceThreads>(sp, tz, 1);
-    if (threadIdx.x == 0) {
-        XYZZ<F> r = mul_small(sgz, kReduceThreads);
-        r.add(sy);
-        r = mul_small(r, K);
-        r.add(sx);
-        r.store(out);
+    s0[g] = g < G ? XYZZ<F>::load(in + 3 * g + 1) : id;
+    block_sum_inplace<F, kReduceThreads>(s0);
+    if (g == 0) res[1] = s0[0];                               // sum Y
+    __syncthreads();
+    s0[g] = g < G ? XYZZ<F>::load(in + 3 * g + 2) : id;
+    XYZZ<F>* T = block_suffix_scan<F, kReduceThreads>(s0, s1);
+    if (g == 0) T[0] = id;
+    block_sum_inplace<F, kReduceThreads>(T);                  // sum_g g*Z_g
+    if (g == 0) {
+        XYZZ<F>* r = &T[0];
+        XYZZ<F>* tmp = &T[1];
+        mul_small_mem(r, tmp, kReduceThreads);
+        xyzz_add_mem(r, r, &res[1]);
+        mul_small_mem(r, tmp, K);
+        xyzz_add_mem(r, r, &res[0]);
+        r->store(out);
     }
 }
 
 // XYZZ (Montgomery) -> affine standard form bytes; identity -> zeros
 template <class F>
 __global__ void k_xyzz_to_affine_std(const XYZZ<F>* in, char* out) {
-    XYZZ<F> p = XYZZ<F>::load(in);
-    Affine<F> a = p.to_affine();
+    Affine<F> a = XYZZ<F>::load(in).to_affine();
     a.x.from_mont().store(out);
     a.y.from_mont().store(out + sizeof(F));
 }
@@ -460,8 +463,8 @@ int bases_build(zkr_ctx* ctx, zkr_bases* b, const char* h_points, size_t n_src, 
     static bool attr_done[2] = {false, false};
     const int which = sizeof(F) == 32 ? 0 : 1;
     if (!attr_done[which]) {
-        ZKR_CUDA(cudaFuncSetAttribute(k_reduce_stage1<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(XB * kReduceThreads)));
-        ZKR_CUDA(cudaFuncSetAttribute(k_reduce_stage2<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(XB * kReduceThreads)));
+        ZKR_CUDA(cudaFuncSetAttribute(k_reduce_stage1<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * XB * kReduceThreads)));
+        ZKR_CUDA(cudaFuncSetAttribute(k_reduce_stage2<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * XB * kReduceThreads)));
         ZKR_CUDA(cudaFuncSetAttribute((k_accum_affine<F, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
         ZKR_CUDA(cudaFuncSetAttribute((k_accum_affine<F, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
         attr_done[which] = true;
@@ -508,7 +511,7 @@ int msm_run(zkr_ctx* ctx, cudaStream_t st, const zkr_bases* b, const uint32_t* d
         ZKR_LAUNCH(ctx, k_accum_xyzz<F>, blocks, 64, 0, st, wk.bnd_keys[cur], (const XYZZ<F>*)wk.bnd[cur],
                    (uint32_t)cnt, kLevelLog, buckets, (XYZZ<F>*)wk.bnd[cur ^ 1], wk.bnd_keys[cur ^ 1], nb, fin);
         if (fin) break;
-        cnt = 2 * (size_t)blocks * 64;
+        cnt = 2 * T;          // threads past T only pad their block; their slots are never read
         cur ^= 1;
     }
     // bucket reduction
@@ -516,8 +519,8 @@ int msm_run(zkr_ctx* ctx, cudaStream_t st, const zkr_bases* b, const uint32_t* d
     if (G < 1) G = 1;
     if (G > 128) G = 128;
     const uint32_t K = (nb + G * kReduceThreads - 1) / (G * kReduceThreads);
-    ZKR_LAUNCH(ctx, k_reduce_stage1<F>, G, kReduceThreads, XB * kReduceThreads, st, buckets, nb, K, (XYZZ<F>*)wk.red);
-    ZKR_LAUNCH(ctx, k_reduce_stage2<F>, 1, kReduceThreads, XB * kReduceThreads, st, (const XYZZ<F>*)wk.red, G, K, d_out);
+    ZKR_LAUNCH(ctx, k_reduce_stage1<F>, G, kReduceThreads, 2 * XB * kReduceThreads, st, buckets, nb, K, (XYZZ<F>*)wk.red);
+    ZKR_LAUNCH(ctx, k_reduce_stage2<F>, 1, kReduceThreads, 2 * XB * kReduceThreads, st, (const XYZZ<F>*)wk.red, G, K, d_out);
     return ZKR_OK;
 }
 

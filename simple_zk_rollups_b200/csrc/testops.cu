@@ -41,15 +41,12 @@ __global__ void k_curve_op(int op, const char* p, const char* q, char* out, size
     } else if (op == 1) {
         acc = acc.dbl();
     } else if (op == 2) {
-        uint32_t k[8];
-        for (int j = 0; j < 8; j++) k[j] = reinterpret_cast<const uint32_t*>(q)[8 * i + j];
-        acc = scalar_mul(acc, k);
+        acc = scalar_mul(acc, Fr::load(q + 32 * i));
     } else {
         Affine<F> Q = Affine<F>::load(q + AB * i);
         XYZZ<F> d = acc.dbl();
-        XYZZ<F> qq = XYZZ<F>::from_affine(Q);
-        qq = qq.dbl();           // non-trivial zz on both operands
-        d.add(qq);               // 2P + 2Q
+        XYZZ<F> qq = XYZZ<F>::from_affine(Q).dbl();            // non-trivial zz on both operands
+        d.add(qq);                                             // 2P + 2Q
         acc = d;
     }
     acc.to_affine().store(out + AB * i);

@@ -8,20 +8,12 @@ import pytest
 from oracle import groth16 as g
 from oracle.bn254 import R
 from simple_zk_rollups_b200 import _lib
+from helpers import pack, unpack
 
 pytestmark = pytest.mark.gpu
 
 FWD, INV, CFWD, CINV = 0, 1, 2, 3
 BR_OUT, BR_IN = 0x10, 0x20
-
-
-def pack(vals):
-    return np.frombuffer(b"".join(int(v).to_bytes(32, "little") for v in vals), dtype=np.uint8).copy()
-
-
-def unpack(arr):
-    b = arr.tobytes()
-    return [int.from_bytes(b[i:i + 32], "little") for i in range(0, len(b), 32)]
 
 
 def brev(x, bits):
