@@ -157,9 +157,11 @@ int zkr_h_from_evals_dev(zkr_ctx* ctx, void* d_a_t, void* d_b_t, int log_m, void
  *   ptr_X[n_vars+1], row_X[nnz], cid_X[nnz] (u32), pool: n_pool x 32 B std form.
  * polsA must already contain the input-consistency rows (snarkjs setup_groth.js).
  * toxic: 5 x 32 B std form (tau, alpha, beta, gamma, delta).
- * Writes the websnark binary proving key (binarify.ts layout) into pk_out (pk_cap bytes; call with
- * pk_out == NULL to get the required size in *pk_len) and the verifying key as raw std-form affine
- * points into vk_out: alfa1 (64) | beta2 (128) | gamma2 (128) | delta2 (128) | IC[n_public+1] (64 each). */
+ * Outputs (host buffers) are the POINT SECTIONS of the websnark binary proving key, encoded exactly
+ * as binarifyProvingKey writes them (affine Fq-M, infinity = (0, R mod q)): out_a / out_b1 (64 n),
+ * out_b2 (128 n), out_c (64 (n - n_public - 1)), out_h (64 domain_size); and out_vk =
+ * alfa1 (64) | beta1 (64) | delta1 (64) | beta2 (128) | gamma2 (128) | delta2 (128) | IC[n_public+1] (64 each),
+ * same encoding.  The host assembles header + pols sections around them (simple_zk_rollups_b200/keygen.py). */
 typedef struct zkr_r1cs_csc {
     uint32_t n_vars, n_public, n_constraints, domain_size, n_pool;
     const uint32_t *ptr_a, *row_a, *cid_a;
@@ -167,8 +169,8 @@ typedef struct zkr_r1cs_csc {
     const uint32_t *ptr_c, *row_c, *cid_c;
     const void* pool;
 } zkr_r1cs_csc;
-int zkr_synth_setup(zkr_ctx* ctx, const zkr_r1cs_csc* r1cs, const void* toxic, void* pk_out,
-                    size_t pk_cap, size_t* pk_len, void* vk_out, size_t vk_cap);
+int zkr_synth_setup(zkr_ctx* ctx, const zkr_r1cs_csc* r1cs, const void* toxic, void* out_a, void* out_b1,
+                    void* out_b2, void* out_c, void* out_h, void* out_vk);
 
 /* ---- test hooks (element-wise field / curve kernels; used by the parity tests) --------- */
 /* field: 0 = Fq, 1 = Fr.  op: 0 mul, 1 add, 2 sub, 3 sqr, 4 inverse, 5 to_mont, 6 from_mont.

@@ -331,3 +331,28 @@ def exponent_check(pk, secrets, witness, proof, r=0, s=0):
     f1, f2 = bn.fixed_base(1), bn.fixed_base(2)
     return (proof["pi_a"] == f1.mul_many([a])[0] and proof["pi_b"] == f2.mul_many([b])[0]
             and proof["pi_c"] == f1.mul_many([c])[0])
+
+
+def exponent_check_flat(mats, pool, n_public, witness, toxic, m, proof, r=0, s=0):
+    """exponent_check for large synthetic circuits: one pass over the sparse entries, no per-signal
+    tables.  mats = {"A": (sig, row, cid)} WITH the input-consistency rows in A; pool = coefficient ints."""
+    tau, alpha, beta, gamma, delta = [x % R for x in toxic]
+    lag = lagrange_at(m, tau)
+    w = [x % R for x in witness]
+    tot, priv = {}, {}
+    for name, (sig, row, cid) in mats.items():
+        t = p = 0
+        for sg, rw, c in zip(sig.tolist(), row.tolist(), cid.tolist()):
+            v = w[sg] * pool[c] % R * lag[rw]
+            t += v
+            if sg > n_public:
+                p += v
+        tot[name], priv[name] = t % R, p % R
+    a = (alpha + tot["A"] + r * delta) % R
+    b = (beta + tot["B"] + s * delta) % R
+    kpriv = (beta * priv["A"] + alpha * priv["B"] + priv["C"]) % R
+    hz = (tot["A"] * tot["B"] - tot["C"]) % R
+    c = ((kpriv + hz) * pow(delta, -1, R) + s * a + r * b - r * s * delta) % R
+    f1, f2 = bn.fixed_base(1), bn.fixed_base(2)
+    return (proof["pi_a"] == f1.mul_many([a])[0] and proof["pi_b"] == f2.mul_many([b])[0]
+            and proof["pi_c"] == f1.mul_many([c])[0])

@@ -1,0 +1,81 @@
+"""Host-side mirror of /root/reference/operator/src/utils/binarify.ts (the websnark wire formats).
+
+Same names, argument meaning and output bytes as the reference's TypeScript:
+  binarifyWitness(witness)        binarify.ts:10-48   -> n x 32 B little-endian, standard form
+  binarifyProvingKey(provingKey)  binarify.ts:50-207  -> websnark binary proving key
+In the reference both run on every proof (common.ts:27-28); here binarifyProvingKey runs once per
+circuit and its output is handed to Groth16Prover.load_key (zkr_pkey_load_bin).
+Inputs follow the snarkjs JSON schema (decimal strings or ints; stringifybigint semantics).
+"""
+import struct
+
+Q = 21888242871839275222246405745257275088696311157297823662689037894645226208583   # binarify.ts:80
+R = 21888242871839275222246405745257275088548364400416034343698204186575808495617   # binarify.ts:87
+_SHIFT = 256                                                                         # binarify.ts:82,89
+
+
+def _big(v):
+    return int(v)
+
+
+def _write_big(v):            # writeBigInt, binarify.ts:68-76: 8 x u32 little-endian
+    return _big(v).to_bytes(32, "little")
+
+
+def _mq(v):                   # toMontgomeryQ, binarify.ts:78-83
+    return (_big(v) << _SHIFT) % Q
+
+
+def _mr(v):                   # toMontgomeryR, binarify.ts:85-90
+    return (_big(v) << _SHIFT) % R
+
+
+def binarifyWitness(witness):
+    return b"".join(_write_big(x) for x in witness)
+
+
+def _point(p):                # writePoint, binarify.ts:92-95 (z is dropped)
+    return _write_big(_mq(p[0])) + _write_big(_mq(p[1]))
+
+
+def _point2(p):               # writePoint2, binarify.ts:97-102
+    return b"".join(_write_big(_mq(v)) for v in (p[0][0], p[0][1], p[1][0], p[1][1]))
+
+
+def _pol(p):                  # writeTransformedPolynomial, binarify.ts:104-113
+    keys = sorted(p, key=int)  # Object.keys of integer-like keys iterates in ascending numeric order
+    out = [struct.pack("<I", len(keys))]
+    for k in keys:
+        out.append(struct.pack("<I", int(k)))
+        out.append(_write_big(_mr(p[k])))
+    return b"".join(out)
+
+
+def binarifyProvingKey(provingKey):
+    pk = provingKey
+    n, l, m = int(pk["nVars"]), int(pk["nPublic"]), int(pk["domainSize"])
+    parts = [_point(pk["vk_alfa_1"]), _point(pk["vk_beta_1"]), _point(pk["vk_delta_1"]),
+             _point2(pk["vk_beta_2"]), _point2(pk["vk_delta_2"])]
+    off = 40 + sum(len(x) for x in parts)
+    ptrs = []
+    for chunks in ((_pol(pk["polsA"][i]) for i in range(n)),
+                   (_pol(pk["polsB"][i]) for i in range(n)),
+                   (_point(pk["A"][i]) for i in range(n)),
+                   (_point(pk["B1"][i]) for i in range(n)),
+                   (_point2(pk["B2"][i]) for i in range(n)),
+                   (_point(pk["C"][i]) for i in range(l + 1, n)),
+                   (_point(pk["hExps"][i]) for i in range(m))):
+        ptrs.append(off)
+        blob = b"".join(chunks)
+        off += len(blob)
+        parts.append(blob)
+    out = struct.pack("<10I", n, l, m, *ptrs) + b"".join(parts)
+    assert len(out) == off                      # binarify.ts:204
+    return out
+
+
+def proof_from_bytes(buf):
+    """256-byte C-ABI proof -> the websnark groth16GenProof result shape (decimal strings)."""
+    v = [str(int.from_bytes(buf[i * 32:(i + 1) * 32], "little")) for i in range(8)]
+    return {"pi_a": [v[0], v[1], "1"], "pi_b": [[v[2], v[3]], [v[4], v[5]], ["1", "0"]],
+            "pi_c": [v[6], v[7], "1"], "protocol": "groth"}

@@ -379,15 +379,19 @@ struct zkr_bases {
 
 namespace zkr {
 
+// h_scalar_idx (nullable): for input point i the index of its scalar in the scalar vector handed to
+// msm_run (default i).  Used by the prover to splice the blinding terms into the key's base sets.
 template <class F>
-int bases_build(zkr_ctx* ctx, zkr_bases* b, const char* h_points, size_t n_src, int c_forced, cudaStream_t st);
+int bases_build(zkr_ctx* ctx, zkr_bases* b, const char* h_points, size_t n_src, int c_forced, cudaStream_t st,
+                const uint32_t* h_scalar_idx = nullptr);
 template <class F>
 int msm_run(zkr_ctx* ctx, cudaStream_t st, const zkr_bases* b, const uint32_t* d_scalars, XYZZ<F>* d_out);
 void bases_release(zkr_bases* b);
 
 // ---------------------------------------------------------------- implementation (header-only, two TUs)
 template <class F>
-int bases_build(zkr_ctx* ctx, zkr_bases* b, const char* h_points, size_t n_src, int c_forced, cudaStream_t st) {
+int bases_build(zkr_ctx* ctx, zkr_bases* b, const char* h_points, size_t n_src, int c_forced, cudaStream_t st,
+                const uint32_t* h_scalar_idx) {
     constexpr size_t AB = 2 * sizeof(F);
     constexpr size_t XB = 4 * sizeof(F);
     b->ctx = ctx;
@@ -412,11 +416,13 @@ int bases_build(zkr_ctx* ctx, zkr_bases* b, const char* h_points, size_t n_src, 
     if (n == 0) return ZKR_OK;
     char* d_pts = nullptr;
     ZKR_CUDA(cudaMalloc(&d_pts, AB * (size_t)n));
-    if (n == n_src) {
+    if (n == n_src && !h_scalar_idx) {
         ZKR_CUDA(cudaMemcpyAsync(d_pts, h_points, AB * (size_t)n, cudaMemcpyHostToDevice, st));
     } else {
         std::vector<char> packed(AB * (size_t)n);
         for (uint32_t k = 0; k < n; k++) memcpy(&packed[AB * k], h_points + AB * idx[k], AB);
+        if (h_scalar_idx)
+            for (uint32_t k = 0; k < n; k++) idx[k] = h_scalar_idx[idx[k]];
         ZKR_CUDA(cudaMemcpyAsync(d_pts, packed.data(), AB * (size_t)n, cudaMemcpyHostToDevice, st));
         ZKR_CUDA(cudaStreamSynchronize(st));
         ZKR_CUDA(cudaMalloc(&b->src_index, 4 * (size_t)n));

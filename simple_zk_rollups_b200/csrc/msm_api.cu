@@ -3,28 +3,7 @@
 #include "common.cuh"
 #include "fp.cuh"
 
-// opaque here: only msm_g1.cu / msm_g2.cu see the templates (keeps this TU cheap to compile)
-struct zkr_bases;
-namespace zkr {
-struct Fq2;
-template <class F> struct XYZZ;
-zkr_bases* bases_alloc();
-int bases_group(const zkr_bases* b);
-zkr_ctx* bases_ctx(const zkr_bases* b);
-void bases_set_group(zkr_bases* b, int g);
-int bases_build_g1(zkr_ctx*, zkr_bases*, const char*, size_t, int, cudaStream_t);
-int bases_build_g2(zkr_ctx*, zkr_bases*, const char*, size_t, int, cudaStream_t);
-int msm_run_g1(zkr_ctx*, cudaStream_t, const zkr_bases*, const uint32_t*, void*);
-int msm_run_g2(zkr_ctx*, cudaStream_t, const zkr_bases*, const uint32_t*, void*);
-int g1_result_to_affine_std(zkr_ctx*, cudaStream_t, const void*, void*);
-int g2_result_to_affine_std(zkr_ctx*, cudaStream_t, const void*, void*);
-void bases_release(zkr_bases* b);
-int bases_range_error(const zkr_bases* b, cudaStream_t st, int* err);
-void bases_info(const zkr_bases* b, uint64_t* n, int* c, int* W, uint64_t* bytes);
-void* bases_result_buf(const zkr_bases* b);
-uint64_t bases_n_src(const zkr_bases* b);
-int bases_peek(const zkr_bases* b, int what, size_t offset, void* out, size_t bytes);
-}  // namespace zkr
+#include "msm_iface.cuh"
 using namespace zkr;
 
 extern "C" int zkr_bases_load(zkr_ctx* ctx, int group, const void* points, size_t n, int window_bits, zkr_bases** out) {
@@ -35,8 +14,8 @@ extern "C" int zkr_bases_load(zkr_ctx* ctx, int group, const void* points, size_
     DeviceGuard g(ctx->device);
     zkr_bases* b = bases_alloc();
     bases_set_group(b, group);
-    int rc = group == 1 ? bases_build_g1(ctx, b, (const char*)points, n, window_bits, ctx->s[0])
-                        : bases_build_g2(ctx, b, (const char*)points, n, window_bits, ctx->s[0]);
+    int rc = group == 1 ? bases_build_g1(ctx, b, (const char*)points, n, window_bits, ctx->s[0], nullptr)
+                        : bases_build_g2(ctx, b, (const char*)points, n, window_bits, ctx->s[0], nullptr);
     if (rc != ZKR_OK) {
         bases_release(b);
         return rc;

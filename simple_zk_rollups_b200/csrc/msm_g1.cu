@@ -1,7 +1,7 @@
 // G1 instantiation of the MSM templates (msm.cuh).
 #include "msm.cuh"
 namespace zkr {
-template int bases_build<Fq>(zkr_ctx*, zkr_bases*, const char*, size_t, int, cudaStream_t);
+template int bases_build<Fq>(zkr_ctx*, zkr_bases*, const char*, size_t, int, cudaStream_t, const uint32_t*);
 template int msm_run<Fq>(zkr_ctx*, cudaStream_t, const zkr_bases*, const uint32_t*, XYZZ<Fq>*);
 int g1_result_to_affine_std(zkr_ctx* ctx, cudaStream_t st, const void* d_xyzz, void* d_out64) {
     ZKR_LAUNCH(ctx, k_xyzz_to_affine_std<Fq>, 1, 1, 0, st, (const XYZZ<Fq>*)d_xyzz, (char*)d_out64);
@@ -23,9 +23,9 @@ void bases_info(const zkr_bases* b, uint64_t* n, int* c, int* W, uint64_t* bytes
     if (W) *W = b->plan.W;
     if (bytes) *bytes = b->bytes;
 }
-int bases_build_g1(zkr_ctx* ctx, zkr_bases* b, const char* p, size_t n, int c, cudaStream_t st) {
+int bases_build_g1(zkr_ctx* ctx, zkr_bases* b, const char* p, size_t n, int c, cudaStream_t st, const uint32_t* sidx) {
     b->ctx = ctx;
-    return bases_build<Fq>(ctx, b, p, n, c, st);
+    return bases_build<Fq>(ctx, b, p, n, c, st, sidx);
 }
 int msm_run_g1(zkr_ctx* ctx, cudaStream_t st, const zkr_bases* b, const uint32_t* sc, void* out) {
     return msm_run<Fq>(ctx, st, b, sc, (XYZZ<Fq>*)out);

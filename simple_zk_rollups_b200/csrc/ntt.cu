@@ -16,30 +16,11 @@
 //     the kernel; the prover chains DIF^-1 -> DIT -> DIF^-1 so no bit-reversal pass is ever run.
 //   * data may be in standard OR Montgomery form: every constant (twiddles, scalings) is stored in
 //     Montgomery form and mont_mul(x, cR) = x*c keeps the form of x.
-#include "common.cuh"
-#include "fp.cuh"
+#include "ntt_iface.cuh"
 
 namespace zkr {
 
 constexpr int kTileLog = 11;
-
-struct NttRoots {
-    Fr w, wi;        // omega_N, omega_N^-1
-    Fr g, gi;        // omega_2N (coset shift), inverse
-    Fr ninv;         // 1/N
-    Fr hconst;       // R/(2N): mont_mul(x/R, .) = x/(2N)   (H pipeline final scaling)
-    Fr one;
-};
-
-struct NttTables {
-    int log_n = 0, kw = 0, lb = 0;
-    NttRoots* roots = nullptr;
-    Fr *wsub_f = nullptr, *wsub_i = nullptr;                              // omega_{2^kw}^{+-j}, j < 2^(kw-1)
-    Fr *tw_lo_f = nullptr, *tw_hi_f = nullptr, *tw_lo_i = nullptr, *tw_hi_i = nullptr;  // omega_N^{+-X}
-    Fr *cs_lo = nullptr, *cs_hi = nullptr, *cs_hi_n = nullptr;            // g^j ; hi / hi * 1/N
-    Fr *ci_lo = nullptr, *ci_hi_n = nullptr, *ci_hi_h = nullptr;          // g^-j ; hi * 1/N ; hi * R/(2N)
-    size_t bytes = 0;
-};
 
 namespace {
 
@@ -50,7 +31,7 @@ __device__ __forceinline__ Fr fr_const(const uint32_t (&l)[8]) {
     return r;
 }
 
-__device__ Fr fr_pow(Fr base, unsigned long long e) {
+__device__ __forceinline__ Fr fr_pow(Fr base, unsigned long long e) {
     Fr acc = Fr::one();
     while (e) {
         if (e & 1) acc = acc * base;

@@ -1,0 +1,506 @@
+// Groth16 prove on one B200: proving-key residency, sparse A_T/B_T, H pipeline, five MSMs, assembly.
+//
+// C-ABI: zkr_pkey_load_bin / zkr_pkey_free / zkr_pkey_info / zkr_prove / zkr_prove_dev / zkr_prove_batch.
+// Replaces, for /root/reference/operator/src/snarks/common.ts:
+//   :28  binarifyProvingKey(provingKey) on every proof  -> zkr_pkey_load_bin once per circuit
+//   :29  wasmBn128.groth16GenProof(witnessBin, pkBin)   -> zkr_prove
+// Math: SURVEY.md Appendix B.2/B.3 (oracle: oracle/groth16.py gen_proof).
+//
+//   pi_a = alfa1 + sum w_i A_i + r delta1            one G1 MSM over [A.., alfa1, delta1] x [w.., 1, r]
+//   pib1 = beta1 + sum w_i B1_i + s delta1           one G1 MSM over [B1.., beta1, delta1] x [w.., 1, s]
+//   pi_b = beta2 + sum w_i B2_i + s delta2           one G2 MSM over [B2.., beta2, delta2] x [w.., 1, s]
+//   pi_c = sum_{i>l} w_i C_i - rs delta1  (one MSM)  +  sum h_j hExps_j (one MSM)  +  s pi_a + r pib1
+// The blinding terms ride inside the MSMs as extra bases, so the only scalar multiplications left
+// are s*pi_a and r*pib1 (two threads, overlapped with the G2 / C / H MSMs on other streams).
+#include <cstring>
+#include <thread>
+
+#include "ec.cuh"
+#include "msm_iface.cuh"
+#include "ntt_iface.cuh"
+
+using namespace zkr;
+
+struct zkr_pkey {
+    zkr_ctx* ctx = nullptr;
+    uint32_t n_vars = 0, n_public = 0, domain_size = 0;
+    int log_m = 0;
+    // polsA / polsB as CSR by constraint row (coefficients Fr-M exactly as in the key)
+    uint32_t *a_ptr = nullptr, *a_sig = nullptr, *b_ptr = nullptr, *b_sig = nullptr;
+    Fr *a_coef = nullptr, *b_coef = nullptr;
+    uint64_t nnz_a = 0, nnz_b = 0;
+    zkr_bases *A = nullptr, *B1 = nullptr, *B2 = nullptr, *C = nullptr, *H = nullptr;
+    // per-proof work buffers (one proof in flight per key)
+    Fr* wext = nullptr;      // [w_0..w_{n-1}, 1, r, s, -rs]  standard form
+    Fr *at = nullptr, *bt = nullptr, *st = nullptr, *h = nullptr;
+    char* res = nullptr;     // XYZZ results: A(128) B1(128) C(128) H(128) T1(128) T2(128) B2(256)
+    char* proof = nullptr;   // 256 B affine standard form
+    int* err = nullptr;      // device flag: witness[0] != 1 or r/s out of range
+    char* rs_dev = nullptr;  // 64 B staging for (r | s)
+    void* pinned = nullptr;  // 256 + 64 B pinned host staging
+    cudaEvent_t ev[16] = {};
+    size_t bytes = 0;
+};
+
+namespace {
+
+enum { R_A = 0, R_B1 = 128, R_C = 256, R_H = 384, R_T1 = 512, R_T2 = 640, R_B2 = 768, R_TOTAL = 1024 };
+
+// A_T[c] = sum_k coef[k] * w[sig[k]]  (coef Montgomery x w standard -> standard)
+__global__ void k_sparse_lc(const uint32_t* __restrict__ a_ptr, const uint32_t* __restrict__ a_sig,
+                            const Fr* __restrict__ a_coef, const uint32_t* __restrict__ b_ptr,
+                            const uint32_t* __restrict__ b_sig, const Fr* __restrict__ b_coef,
+                            const Fr* __restrict__ w, Fr* __restrict__ at, Fr* __restrict__ bt, uint32_t m) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= m) return;
+    const bool isb = blockIdx.y != 0;
+    const uint32_t* ptr = isb ? b_ptr : a_ptr;
+    const uint32_t* sig = isb ? b_sig : a_sig;
+    const Fr* coef = isb ? b_coef : a_coef;
+    Fr acc = Fr::zero();
+    const uint32_t e = ptr[c + 1];
+    for (uint32_t k = ptr[c]; k < e; k++) acc = acc + Fr::load_ro(coef + k) * Fr::load_ro(w + sig[k]);
+    acc.store((isb ? bt : at) + c);
+}
+
+// wext[n] = 1, wext[n+1] = r, wext[n+2] = s, wext[n+3] = -(r s) mod r_order; validates w_0, r, s
+__global__ void k_prep_scalars(Fr* wext, uint32_t n, const Fr* rs, int* err) {
+    Fr r = Fr::load(rs), s = Fr::load(rs + 1);
+    if (!r.in_range() || !s.in_range()) *err = 1;
+    Fr one = Fr::zero();
+    one.v[0] = 1;
+    if (Fr::load(wext) != one) *err = 2;
+    Fr rsm = (r.to_mont() * s.to_mont()).from_mont();
+    one.store(wext + n);
+    r.store(wext + n + 1);
+    s.store(wext + n + 2);
+    rsm.neg().store(wext + n + 3);
+}
+
+// every witness value must be < r (signals that touch no base are read by no MSM)
+__global__ void k_witness_range(const Fr* __restrict__ w, uint32_t n, int* err) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && !Fr::load_ro(w + i).in_range()) *err = 1;
+}
+
+// block 0: T1 = s * pi_a ; block 1: T2 = r * pib1
+__global__ void k_blind_muls(char* res, const Fr* wext, uint32_t n) {
+    const bool second = blockIdx.x != 0;
+    G1XYZZ p = G1XYZZ::load(res + (second ? R_B1 : R_A));
+    Fr k = Fr::load(wext + n + (second ? 1 : 2));
+    scalar_mul(p, k).store(res + (second ? R_T2 : R_T1));
+}
+
+// block 0: pi_a, block 1: pi_b, block 2: pi_c = C + H + T1 + T2; affine, standard form
+__global__ void k_finish(const char* res, char* proof) {
+    if (blockIdx.x == 0) {
+        G1Affine a = G1XYZZ::load(res + R_A).to_affine();
+        a.x.from_mont().store(proof);
+        a.y.from_mont().store(proof + 32);
+    } else if (blockIdx.x == 1) {
+        G2Affine a = G2XYZZ::load(res + R_B2).to_affine();
+        a.x.from_mont().store(proof + 64);
+        a.y.from_mont().store(proof + 128);
+    } else {
+        G1XYZZ c = G1XYZZ::load(res + R_C);
+#pragma unroll 1
+        for (int i = 0; i < 3; i++) c.add(G1XYZZ::load(res + (i == 0 ? R_H : (i == 1 ? R_T1 : R_T2))));
+        G1Affine a = c.to_affine();
+        a.x.from_mont().store(proof + 192);
+        a.y.from_mont().store(proof + 224);
+    }
+}
+
+struct PkView {
+    uint32_t n, l, m, pA, pB, pPA, pPB1, pPB2, pPC, pPH;
+};
+
+bool is_pow2(uint32_t x) { return x && !(x & (x - 1)); }
+
+// walk one pols section (binarify.ts:104-113): per signal u32 count, then count x (u32 row, 32 B coef)
+int pols_to_csr(const uint8_t* buf, size_t len, size_t off, size_t end, uint32_t n, uint32_t m,
+                std::vector<uint32_t>& ptr, std::vector<uint32_t>& sig, std::vector<uint8_t>& coef) {
+    ptr.assign((size_t)m + 1, 0);
+    size_t o = off;
+    uint64_t nnz = 0;
+    for (uint32_t s = 0; s < n; s++) {
+        if (o + 4 > end) return ZKR_E_BADKEY;
+        uint32_t k;
+        memcpy(&k, buf + o, 4);
+        o += 4;
+        if ((uint64_t)k * 36 > end - o) return ZKR_E_BADKEY;
+        for (uint32_t j = 0; j < k; j++) {
+            uint32_t row;
+            memcpy(&row, buf + o + 36ull * j, 4);
+            if (row >= m) return ZKR_E_BADKEY;
+            ptr[row + 1]++;
+        }
+        o += 36ull * k;
+        nnz += k;
+    }
+    if (o != end) return ZKR_E_BADKEY;
+    for (uint32_t c = 0; c < m; c++) ptr[c + 1] += ptr[c];
+    sig.resize(nnz);
+    coef.resize(nnz * 32);
+    std::vector<uint32_t> cur(ptr.begin(), ptr.end() - 1);
+    o = off;
+    for (uint32_t s = 0; s < n; s++) {
+        uint32_t k;
+        memcpy(&k, buf + o, 4);
+        o += 4;
+        for (uint32_t j = 0; j < k; j++) {
+            uint32_t row;
+            memcpy(&row, buf + o, 4);
+            const uint32_t d = cur[row]++;
+            sig[d] = s;
+            memcpy(&coef[32ull * d], buf + o + 4, 32);
+            o += 36;
+        }
+    }
+    (void)len;
+    return ZKR_OK;
+}
+
+int upload(const void* h, size_t bytes, void** d, cudaStream_t st, size_t* total) {
+    ZKR_CUDA(cudaMalloc(d, bytes ? bytes : 16));
+    if (bytes) ZKR_CUDA(cudaMemcpyAsync(*d, h, bytes, cudaMemcpyHostToDevice, st));
+    ZKR_CUDA(cudaStreamSynchronize(st));
+    *total += bytes;
+    return ZKR_OK;
+}
+
+void pkey_release(zkr_pkey* pk) {
+    if (!pk) return;
+    void* ps[] = {pk->a_ptr, pk->a_sig, pk->a_coef, pk->b_ptr, pk->b_sig, pk->b_coef, pk->wext, pk->at, pk->bt,
+                  pk->st, pk->h, pk->res, pk->proof, pk->err, pk->rs_dev};
+    for (void* p : ps) cudaFree(p);
+    if (pk->pinned) cudaFreeHost(pk->pinned);
+    for (auto& e : pk->ev)
+        if (e) cudaEventDestroy(e);
+    zkr_bases* bs[] = {pk->A, pk->B1, pk->B2, pk->C, pk->H};
+    for (zkr_bases* b : bs) bases_release(b);
+    delete pk;
+}
+
+}  // namespace
+
+extern "C" int zkr_pkey_load_bin(zkr_ctx* ctx, const void* vbuf, size_t len, zkr_pkey** out) {
+    if (!ctx || !vbuf || !out) return ZKR_E_INVALID;
+    *out = nullptr;
+    const uint8_t* buf = (const uint8_t*)vbuf;
+    if (len < 488) {
+        set_error("proving key too short (%zu bytes)", len);
+        return ZKR_E_BADKEY;
+    }
+    PkView v;
+    memcpy(&v, buf, 40);
+    const uint64_t n = v.n, l = v.l, m = v.m;
+    bool ok = n >= 1 && l + 1 <= n && is_pow2(v.m) && m >= 2 && m <= (1u << 27) && v.pA == 488 && v.pA <= v.pB &&
+              v.pB <= v.pPA && v.pPA <= len;
+    ok = ok && (uint64_t)v.pPA + 64 * n == v.pPB1 && (uint64_t)v.pPB1 + 64 * n == v.pPB2 &&
+         (uint64_t)v.pPB2 + 128 * n == v.pPC && (uint64_t)v.pPC + 64 * (n - l - 1) == v.pPH &&
+         (uint64_t)v.pPH + 64 * m == len;
+    if (!ok) {
+        set_error("proving key header inconsistent (nVars=%u nPublic=%u domainSize=%u len=%zu)", v.n, v.l, v.m, len);
+        return ZKR_E_BADKEY;
+    }
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = ctx->s[0];
+    zkr_pkey* pk = new zkr_pkey();
+    pk->ctx = ctx;
+    pk->n_vars = v.n;
+    pk->n_public = v.l;
+    pk->domain_size = v.m;
+    while ((1u << pk->log_m) < v.m) pk->log_m++;
+    int rc = ZKR_OK;
+#define PK_TRY(expr)              \
+    do {                          \
+        rc = (expr);              \
+        if (rc != ZKR_OK) {       \
+            pkey_release(pk);     \
+            return rc;            \
+        }                         \
+    } while (0)
+    {   // polsA, polsB -> CSR
+        std::vector<uint32_t> ptr, sig;
+        std::vector<uint8_t> coef;
+        rc = pols_to_csr(buf, len, v.pA, v.pB, v.n, v.m, ptr, sig, coef);
+        if (rc != ZKR_OK) {
+            set_error("polsA section malformed");
+            pkey_release(pk);
+            return rc;
+        }
+        pk->nnz_a = sig.size();
+        PK_TRY(upload(ptr.data(), ptr.size() * 4, (void**)&pk->a_ptr, st, &pk->bytes));
+        PK_TRY(upload(sig.data(), sig.size() * 4, (void**)&pk->a_sig, st, &pk->bytes));
+        PK_TRY(upload(coef.data(), coef.size(), (void**)&pk->a_coef, st, &pk->bytes));
+        rc = pols_to_csr(buf, len, v.pB, v.pPA, v.n, v.m, ptr, sig, coef);
+        if (rc != ZKR_OK) {
+            set_error("polsB section malformed");
+            pkey_release(pk);
+            return rc;
+        }
+        pk->nnz_b = sig.size();
+        PK_TRY(upload(ptr.data(), ptr.size() * 4, (void**)&pk->b_ptr, st, &pk->bytes));
+        PK_TRY(upload(sig.data(), sig.size() * 4, (void**)&pk->b_sig, st, &pk->bytes));
+        PK_TRY(upload(coef.data(), coef.size(), (void**)&pk->b_coef, st, &pk->bytes));
+    }
+    const uint8_t *alfa1 = buf + 40, *beta1 = buf + 104, *delta1 = buf + 168, *beta2 = buf + 232, *delta2 = buf + 360;
+    const uint32_t N = v.n;
+    {   // A' = [A.., alfa1, delta1] x [w.., 1, r]
+        std::vector<char> pts(64ull * (n + 2));
+        memcpy(pts.data(), buf + v.pPA, 64 * n);
+        memcpy(&pts[64 * n], alfa1, 64);
+        memcpy(&pts[64 * (n + 1)], delta1, 64);
+        std::vector<uint32_t> sidx(n + 2);
+        for (uint32_t i = 0; i < N + 2; i++) sidx[i] = i;            // n -> 1, n+1 -> r
+        pk->A = bases_alloc();
+        bases_set_group(pk->A, 1);
+        PK_TRY(bases_build_g1(ctx, pk->A, pts.data(), n + 2, 0, st, sidx.data()));
+        // B1' = [B1.., beta1, delta1] x [w.., 1, s]
+        memcpy(pts.data(), buf + v.pPB1, 64 * n);
+        memcpy(&pts[64 * n], beta1, 64);
+        sidx[N + 1] = N + 2;                                          // s
+        pk->B1 = bases_alloc();
+        bases_set_group(pk->B1, 1);
+        PK_TRY(bases_build_g1(ctx, pk->B1, pts.data(), n + 2, 0, st, sidx.data()));
+        // B2' = [B2.., beta2, delta2] x [w.., 1, s]
+        std::vector<char> pts2(128ull * (n + 2));
+        memcpy(pts2.data(), buf + v.pPB2, 128 * n);
+        memcpy(&pts2[128 * n], beta2, 128);
+        memcpy(&pts2[128 * (n + 1)], delta2, 128);
+        pk->B2 = bases_alloc();
+        bases_set_group(pk->B2, 2);
+        PK_TRY(bases_build_g2(ctx, pk->B2, pts2.data(), n + 2, 0, st, sidx.data()));
+    }
+    {   // C' = [C_{l+1}.., delta1] x [w_{l+1}.., -rs]
+        const uint64_t nc = n - l - 1;
+        std::vector<char> pts(64ull * (nc + 1));
+        memcpy(pts.data(), buf + v.pPC, 64 * nc);
+        memcpy(&pts[64 * nc], delta1, 64);
+        std::vector<uint32_t> sidx(nc + 1);
+        for (uint64_t i = 0; i < nc; i++) sidx[i] = (uint32_t)(l + 1 + i);
+        sidx[nc] = N + 3;
+        pk->C = bases_alloc();
+        bases_set_group(pk->C, 1);
+        PK_TRY(bases_build_g1(ctx, pk->C, pts.data(), nc + 1, 0, st, sidx.data()));
+    }
+    {   // H: hExps permuted to bit-reversed order (the H pipeline leaves h bit-reversed)
+        std::vector<char> pts(64ull * m);
+        const int lg = pk->log_m;
+        for (uint64_t p = 0; p < m; p++) {
+            uint32_t j = 0;
+            for (int b = 0; b < lg; b++) j |= ((p >> b) & 1u) << (lg - 1 - b);
+            memcpy(&pts[64 * p], buf + v.pPH + 64ull * j, 64);
+        }
+        pk->H = bases_alloc();
+        bases_set_group(pk->H, 1);
+        PK_TRY(bases_build_g1(ctx, pk->H, pts.data(), m, 0, st, nullptr));
+    }
+    // work buffers
+    auto dmalloc = [&](void** p, size_t bytes) -> int {
+        ZKR_CUDA(cudaMalloc(p, bytes));
+        pk->bytes += bytes;
+        return ZKR_OK;
+    };
+    PK_TRY(dmalloc((void**)&pk->wext, 32 * (n + 4)));
+    PK_TRY(dmalloc((void**)&pk->at, 32 * m));
+    PK_TRY(dmalloc((void**)&pk->bt, 32 * m));
+    PK_TRY(dmalloc((void**)&pk->st, 32 * m));
+    PK_TRY(dmalloc((void**)&pk->h, 32 * m));
+    PK_TRY(dmalloc((void**)&pk->res, R_TOTAL));
+    PK_TRY(dmalloc((void**)&pk->proof, ZKR_PROOF_BYTES));
+    PK_TRY(dmalloc((void**)&pk->err, sizeof(int)));
+    PK_TRY(dmalloc((void**)&pk->rs_dev, 64));
+    if (cudaMallocHost(&pk->pinned, 512) != cudaSuccess) {
+        pkey_release(pk);
+        return ZKR_E_NOMEM;
+    }
+    cudaMemsetAsync(pk->err, 0, sizeof(int), st);
+    for (auto& e : pk->ev) cudaEventCreate(&e);
+    NttTables* t;
+    PK_TRY(ntt_get_tables(ctx, pk->log_m, &t));
+    zkr_bases* bs[] = {pk->A, pk->B1, pk->B2, pk->C, pk->H};
+    for (zkr_bases* b : bs) {
+        uint64_t bb = 0;
+        bases_info(b, nullptr, nullptr, nullptr, &bb);
+        pk->bytes += bb;
+    }
+    cudaStreamSynchronize(st);
+#undef PK_TRY
+    *out = pk;
+    return ZKR_OK;
+}
+
+extern "C" void zkr_pkey_free(zkr_pkey* pk) {
+    if (!pk) return;
+    DeviceGuard g(pk->ctx->device);
+    cudaDeviceSynchronize();
+    pkey_release(pk);
+}
+
+extern "C" int zkr_pkey_info(const zkr_pkey* pk, uint32_t* n_vars, uint32_t* n_public, uint32_t* domain_size,
+                             uint64_t* device_bytes) {
+    if (!pk) return ZKR_E_INVALID;
+    if (n_vars) *n_vars = pk->n_vars;
+    if (n_public) *n_public = pk->n_public;
+    if (domain_size) *domain_size = pk->domain_size;
+    if (device_bytes) *device_bytes = pk->bytes;
+    return ZKR_OK;
+}
+
+// Queue one proof: witness already in pk->wext[0..n), (r|s) in pk->rs_dev.  Result -> d_proof.
+static int prove_enqueue(zkr_ctx* ctx, const zkr_pkey* pk, char* d_proof, bool timed) {
+    const uint32_t n = pk->n_vars, m = pk->domain_size;
+    cudaStream_t us = ctx->user_stream;
+    cudaEvent_t const* ev = pk->ev;
+    ZKR_LAUNCH(ctx, k_prep_scalars, 1, 1, 0, us, pk->wext, n, (const Fr*)pk->rs_dev, pk->err);
+    ZKR_LAUNCH(ctx, k_witness_range, ceil_div(n, 256), 256, 0, us, pk->wext, n, pk->err);
+    ZKR_TRY(ctx->fork(5));
+    cudaStream_t sH = ctx->s[0], sA = ctx->s[1], sB1 = ctx->s[2], sB2 = ctx->s[3], sC = ctx->s[4];
+    const uint32_t* w = (const uint32_t*)pk->wext;
+    // heaviest first: the G2 MSM costs ~3 G1 MSMs
+    if (timed) cudaEventRecord(ev[6], sB2);
+    ZKR_TRY(msm_run_g2(ctx, sB2, pk->B2, w, pk->res + R_B2));
+    if (timed) cudaEventRecord(ev[7], sB2);
+    // H chain
+    if (timed) cudaEventRecord(ev[0], sH);
+    ZKR_LAUNCH(ctx, k_sparse_lc, dim3(ceil_div(m, 128), 2), 128, 0, sH, pk->a_ptr, pk->a_sig, pk->a_coef, pk->b_ptr,
+               pk->b_sig, pk->b_coef, pk->wext, pk->at, pk->bt, m);
+    if (timed) cudaEventRecord(ev[1], sH);
+    ZKR_TRY(h_pipeline(ctx, sH, pk->at, pk->bt, pk->st, pk->h, pk->log_m, true));
+    if (timed) cudaEventRecord(ev[2], sH);
+    ZKR_TRY(msm_run_g1(ctx, sH, pk->H, (const uint32_t*)pk->h, pk->res + R_H));
+    if (timed) cudaEventRecord(ev[3], sH);
+    // A, then s * pi_a
+    if (timed) cudaEventRecord(ev[4], sA);
+    ZKR_TRY(msm_run_g1(ctx, sA, pk->A, w, pk->res + R_A));
+    if (timed) cudaEventRecord(ev[5], sA);
+    if (timed) cudaEventRecord(ev[8], sB1);
+    ZKR_TRY(msm_run_g1(ctx, sB1, pk->B1, w, pk->res + R_B1));
+    if (timed) cudaEventRecord(ev[9], sB1);
+    if (timed) cudaEventRecord(ev[10], sC);
+    ZKR_TRY(msm_run_g1(ctx, sC, pk->C, w, pk->res + R_C));
+    if (timed) cudaEventRecord(ev[11], sC);
+    // the two blinding scalar multiplications need A and B1
+    ZKR_CUDA(cudaEventRecord(ctx->ev_join[2], sB1));
+    ZKR_CUDA(cudaStreamWaitEvent(sA, ctx->ev_join[2], 0));
+    ZKR_LAUNCH(ctx, k_blind_muls, 2, 1, 0, sA, pk->res, pk->wext, n);
+    ZKR_TRY(ctx->join(5));
+    if (timed) cudaEventRecord(ev[12], us);
+    ZKR_LAUNCH(ctx, k_finish, 3, 1, 0, us, (const char*)pk->res, d_proof);
+    if (timed) cudaEventRecord(ev[13], us);
+    return ZKR_OK;
+}
+
+static int check_range_flags(zkr_ctx* ctx, const zkr_pkey* pk) {
+    int e = 0;
+    ZKR_CUDA(cudaMemcpyAsync(&e, pk->err, sizeof(int), cudaMemcpyDeviceToHost, ctx->user_stream));
+    ZKR_CUDA(cudaStreamSynchronize(ctx->user_stream));
+    int any = e;
+    const zkr_bases* bs[] = {pk->A, pk->B1, pk->B2, pk->C, pk->H};
+    for (const zkr_bases* b : bs) {
+        int be = 0;
+        ZKR_TRY(bases_range_error(b, ctx->user_stream, &be));
+        any |= be;
+    }
+    if (e) ZKR_CUDA(cudaMemsetAsync(pk->err, 0, sizeof(int), ctx->user_stream));
+    if (any) {
+        set_error(e == 2 ? "witness[0] must be 1" : "a witness value or blinding scalar is >= r");
+        return ZKR_E_WITNESS_RANGE;
+    }
+    return ZKR_OK;
+}
+
+extern "C" int zkr_prove(zkr_ctx* ctx, const zkr_pkey* pk, const void* witness, size_t n_signals, const void* r32,
+                         const void* s32, void* out_proof, zkr_stats* stats) {
+    if (!ctx || !pk || !witness || !out_proof || pk->ctx != ctx) return ZKR_E_INVALID;
+    if (n_signals != pk->n_vars) {
+        set_error("witness has %zu signals, key expects %u", n_signals, pk->n_vars);
+        return ZKR_E_INVALID;
+    }
+    DeviceGuard g(ctx->device);
+    cudaStream_t us = ctx->user_stream;
+    const uint64_t launches0 = ctx->launches;
+    char* pin = (char*)pk->pinned;
+    memset(pin + 256, 0, 64);
+    if (r32) memcpy(pin + 256, r32, 32);
+    if (s32) memcpy(pin + 288, s32, 32);
+    cudaEvent_t const* ev = pk->ev;
+    cudaEventRecord(ev[14], us);
+    ZKR_CUDA(cudaMemcpyAsync(pk->wext, witness, 32ull * pk->n_vars, cudaMemcpyHostToDevice, us));
+    ZKR_CUDA(cudaMemcpyAsync(pk->rs_dev, pin + 256, 64, cudaMemcpyHostToDevice, us));
+    ZKR_TRY(prove_enqueue(ctx, pk, pk->proof, true));
+    ZKR_CUDA(cudaMemcpyAsync(pin, pk->proof, ZKR_PROOF_BYTES, cudaMemcpyDeviceToHost, us));
+    cudaEventRecord(ev[15], us);
+    ZKR_CUDA(cudaStreamSynchronize(us));
+    int rc = check_range_flags(ctx, pk);
+    if (rc != ZKR_OK) return rc;
+    memcpy(out_proof, pin, ZKR_PROOF_BYTES);
+    zkr_stats s = {};
+    auto el = [&](int a, int b) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ev[a], ev[b]);
+        return ms;
+    };
+    s.total_ms = el(14, 15);
+    s.h2d_ms = 0;   // included in total; the copy is queued ahead of the first kernel on the same stream
+    s.lc_ms = el(0, 1);
+    s.ntt_ms = el(1, 2);
+    s.msm_h_ms = el(2, 3);
+    s.msm_a_ms = el(4, 5);
+    s.msm_b2_ms = el(6, 7);
+    s.msm_b1_ms = el(8, 9);
+    s.msm_c_ms = el(10, 11);
+    s.assemble_ms = el(12, 13);
+    s.kernel_launches = ctx->launches - launches0;
+    ctx->last_stats = s;
+    if (stats) *stats = s;
+    return ZKR_OK;
+}
+
+extern "C" int zkr_prove_dev(zkr_ctx* ctx, const zkr_pkey* pk, const void* d_witness, size_t n_signals,
+                             const void* r32, const void* s32, void* d_out_proof) {
+    if (!ctx || !pk || !d_witness || !d_out_proof || pk->ctx != ctx || n_signals != pk->n_vars) return ZKR_E_INVALID;
+    DeviceGuard g(ctx->device);
+    cudaStream_t us = ctx->user_stream;
+    char* pin = (char*)pk->pinned;
+    // the staging words are re-used per call: wait for the previous call's copy to have been consumed
+    ZKR_CUDA(cudaStreamSynchronize(us));
+    memset(pin + 256, 0, 64);
+    if (r32) memcpy(pin + 256, r32, 32);
+    if (s32) memcpy(pin + 288, s32, 32);
+    ZKR_CUDA(cudaMemcpyAsync(pk->wext, d_witness, 32ull * pk->n_vars, cudaMemcpyDeviceToDevice, us));
+    ZKR_CUDA(cudaMemcpyAsync(pk->rs_dev, pin + 256, 64, cudaMemcpyHostToDevice, us));
+    return prove_enqueue(ctx, pk, (char*)d_out_proof, false);
+}
+
+extern "C" int zkr_prove_batch(zkr_ctx* const* ctxs, const zkr_pkey* const* pks, int n_ctx,
+                               const void* const* witnesses, size_t n_signals, int n_proofs, const void* rs32,
+                               void* out_proofs) {
+    if (!ctxs || !pks || n_ctx < 1 || !witnesses || n_proofs < 0 || !out_proofs) return ZKR_E_INVALID;
+    std::vector<int> rcs(n_ctx, ZKR_OK);
+    std::vector<std::string> msgs(n_ctx);
+    std::vector<std::thread> th;
+    for (int c = 0; c < n_ctx; c++) {
+        th.emplace_back([&, c]() {
+            for (int i = c; i < n_proofs; i += n_ctx) {
+                const char* rs = rs32 ? (const char*)rs32 + 64ull * i : nullptr;
+                int rc = zkr_prove(ctxs[c], pks[c], witnesses[i], n_signals, rs, rs ? rs + 32 : nullptr,
+                                   (char*)out_proofs + (size_t)ZKR_PROOF_BYTES * i, nullptr);
+                if (rc != ZKR_OK) {
+                    rcs[c] = rc;
+                    msgs[c] = zkr_last_error();
+                    return;
+                }
+            }
+        });
+    }
+    for (auto& t : th) t.join();
+    for (int c = 0; c < n_ctx; c++)
+        if (rcs[c] != ZKR_OK) {
+            set_error("proof batch failed on context %d: %s", c, msgs[c].c_str());
+            return rcs[c];
+        }
+    return ZKR_OK;
+}

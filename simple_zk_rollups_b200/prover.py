@@ -1,0 +1,135 @@
+"""Python host mirror of the reference's proof-generator API, backed by libzkr (CUDA, sm_100a).
+
+Reference surface kept (operator/src/snarks/common.ts:10-53, tx.ts:6-10, withdraw.ts:6-10):
+    createProofGenerator(provingKey, verifyingKey, circuitName) -> async (circuitInputs) ->
+        {proof, solidityProof: {a, b, c, inputs}}
+and the snarkjs-shaped call the north star names:
+    genProof(provingKey, witness) -> {proof: {pi_a, pi_b, pi_c, protocol}, publicSignals}
+What changes underneath: common.ts:23 (buildBn128), :28 (binarifyProvingKey per proof) and :29
+(groth16GenProof) become one resident key + zkr_prove.  Witness generation (common.ts:12-21) and the
+self-verification (common.ts:30-38) stay host-side callables exactly as they stay TypeScript in the
+reference; circom cannot run here, so the witness calculator is an injected callable.
+No CPU fallback: every prove goes through the CUDA library or raises.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .binarify import R as SNARK_FIELD_SIZE
+from .binarify import binarifyProvingKey, binarifyWitness, proof_from_bytes
+
+
+class Groth16Prover:
+    """One libzkr context (one GPU) with proving keys resident in HBM."""
+
+    def __init__(self, device=0):
+        self.L = _lib.lib()
+        self.ctx = C.c_void_p()
+        _lib.check(self.L.zkr_ctx_create(device, C.byref(self.ctx)))
+        self.device = device
+        self._keys = []
+
+    def close(self):
+        for k in self._keys:
+            self.L.zkr_pkey_free(k)
+        self._keys = []
+        if self.ctx:
+            self.L.zkr_ctx_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def load_key(self, pk_bin):
+        """pk_bin: bytes / numpy uint8 in the binarifyProvingKey layout.  Parsed + uploaded once."""
+        arr = np.frombuffer(pk_bin, dtype=np.uint8) if isinstance(pk_bin, (bytes, bytearray)) else pk_bin
+        h = C.c_void_p()
+        _lib.check(self.L.zkr_pkey_load_bin(self.ctx, _lib.buf_ptr(arr), arr.size, C.byref(h)))
+        self._keys.append(h)
+        return h
+
+    def key_info(self, key):
+        a, b, c, d = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint64()
+        _lib.check(self.L.zkr_pkey_info(key, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return dict(nVars=a.value, nPublic=b.value, domainSize=c.value, device_bytes=d.value)
+
+    def prove(self, key, witness_bin, r=0, s=0):
+        """witness_bin: binarifyWitness output.  r, s: blinding scalars (ints < r); (0, 0) is the
+        snarkjs debug mode.  -> (256-byte proof, stats dict)."""
+        w = np.frombuffer(witness_bin, dtype=np.uint8) if isinstance(witness_bin, (bytes, bytearray)) else witness_bin
+        out = np.zeros(_lib.PROOF_BYTES, dtype=np.uint8)
+        st = _lib.Stats()
+        rb = np.frombuffer(int(r).to_bytes(32, "little"), dtype=np.uint8)
+        sb = np.frombuffer(int(s).to_bytes(32, "little"), dtype=np.uint8)
+        _lib.check(self.L.zkr_prove(self.ctx, key, _lib.buf_ptr(w), w.size // 32, _lib.buf_ptr(rb),
+                                    _lib.buf_ptr(sb), _lib.buf_ptr(out), C.byref(st)))
+        return out.tobytes(), st.as_dict()
+
+    def kernel_launches(self):
+        return int(self.L.zkr_ctx_kernel_launches(self.ctx))
+
+
+_default = None
+
+
+def default_prover():
+    global _default
+    if _default is None:
+        _default = Groth16Prover(0)
+    return _default
+
+
+def _random_scalar():
+    import secrets
+    return secrets.randbelow(SNARK_FIELD_SIZE)
+
+
+def genProof(provingKey, witness, r=None, s=None, prover=None, _key_cache={}):
+    """snarkjs groth.genProof shape: -> {"proof": {pi_a, pi_b, pi_c, protocol}, "publicSignals": [...]}.
+    provingKey: snarkjs pk JSON (dict) or an already-binarified key (bytes / uint8 array).
+    r, s default to CSPRNG draws like websnark; pass 0, 0 for the snarkjs debug mode."""
+    p = prover or default_prover()
+    if isinstance(provingKey, dict):
+        ck = id(provingKey)
+        if ck not in _key_cache:
+            _key_cache[ck] = (p.load_key(binarifyProvingKey(provingKey)), int(provingKey["nPublic"]))
+        key, n_public = _key_cache[ck]
+    else:
+        key = p.load_key(provingKey)
+        n_public = p.key_info(key)["nPublic"]
+    r = _random_scalar() if r is None else r
+    s = _random_scalar() if s is None else s
+    buf, _ = p.prove(key, binarifyWitness(witness), r, s)
+    return {"proof": proof_from_bytes(buf), "publicSignals": [str(int(x)) for x in witness[1:n_public + 1]]}
+
+
+def createProofGenerator(provingKey, verifyingKey, circuitName, calculateWitness, isValid=None, prover=None):
+    """Mirror of operator/src/snarks/common.ts:10-53.
+
+    calculateWitness(circuitName, circuitInputs) -> (witness: list[int], nPubInputs_plus_nOutputs: int)
+        stands for circom compile + snarkjs Circuit.calculateWitness (common.ts:12-21), which stay
+        on the host in the reference as well.
+    isValid(verifyingKey, proof, publicSignals) -> bool stands for snarkjs groth.isValid
+        (common.ts:30-34); when given, an invalid proof raises "Invalid proof generated" (common.ts:36-38).
+    The returned callable is synchronous; the reference's is async only because websnark is."""
+    p = prover or default_prover()
+    key = p.load_key(binarifyProvingKey(provingKey) if isinstance(provingKey, dict) else provingKey)
+
+    def generate(circuitInputs, r=None, s=None):
+        witness, n_pub = calculateWitness(circuitName, circuitInputs)
+        publicSignals = witness[1:n_pub + 1]
+        rr = _random_scalar() if r is None else r
+        ss = _random_scalar() if s is None else s
+        buf, _ = p.prove(key, binarifyWitness(witness), rr, ss)
+        proof = proof_from_bytes(buf)
+        if isValid is not None and not isValid(verifyingKey, proof, publicSignals):
+            raise RuntimeError("Invalid proof generated")
+        return {
+            "proof": proof,
+            "solidityProof": {                       # common.ts:42-50
+                "a": proof["pi_a"][:2],
+                "b": [list(reversed(x)) for x in proof["pi_b"]][:2],
+                "c": proof["pi_c"][:2],
+                "inputs": [str(int(x) % SNARK_FIELD_SIZE) for x in publicSignals],
+            },
+        }
+
+    return generate

@@ -1,0 +1,165 @@
+"""GPU parity for the whole hot path: zkr_prove vs the oracle's gen_proof, byte for byte with fixed (r, s);
+the proof must verify under the restated on-chain predicate (TxVerifier.sol:258-276) and a tampered
+public input must fail (contracts/__tests__/withdrawverifier.test.ts:42-68)."""
+import random
+import time
+
+import numpy as np
+import pytest
+
+from oracle import binfmt as bf
+from oracle import groth16 as g
+from oracle.bn254 import R
+from simple_zk_rollups_b200 import _lib, binarify, keygen, prover, synth
+
+pytestmark = pytest.mark.gpu
+
+TOXIC = (0x1234567890ABCDEF1234567890ABCDEF1234567, 0x2222222222222222222222222222222222221,
+         0x3333333333333333333333333333333333333331, 0x44444444444444444444444444444444441,
+         0x555555555555555555555555555555555555555551)
+
+
+@pytest.fixture(scope="module")
+def gp():
+    p = prover.Groth16Prover(0)
+    yield p
+    p.close()
+
+
+@pytest.mark.parametrize("nc,npub,seed", [(5, 1, 1), (50, 3, 2), (200, 10, 3), (1000, 4, 4)])
+def test_prove_bit_exact_small(gp, nc, npub, seed):
+    r1, w = synth.generate(nc, npub, seed=seed)
+    pk, vk, sec = g.setup(r1.to_dicts(), TOXIC)
+    key = gp.load_key(bf.binarify_proving_key(pk))
+    info = gp.key_info(key)
+    assert (info["nVars"], info["nPublic"], info["domainSize"]) == (pk["nVars"], pk["nPublic"], pk["domainSize"])
+    wbin = bf.binarify_witness(w)
+    rng = random.Random(seed)
+    for r, s in ((0, 0), (1, 0), (0, 1), (rng.randrange(R), rng.randrange(R)), (R - 1, R - 1)):
+        got, stats = gp.prove(key, wbin, r, s)
+        want, pub = g.gen_proof(pk, w, r, s)
+        assert got == g.proof_to_bytes(want), "proof bytes differ at (r,s)=(%d,%d)" % (r, s)
+        assert stats["kernel_launches"] > 0
+    proof = g.proof_from_bytes(got)
+    assert g.verify(vk, proof, pub)
+    bad = list(pub)
+    bad[0] = (bad[0] + 1) % R
+    assert not g.verify(vk, proof, bad)
+    assert g.exponent_check(pk, sec, w, proof, R - 1, R - 1)
+
+
+def test_prove_rejects_bad_inputs(gp):
+    r1, w = synth.generate(20, 2, seed=9)
+    pk, vk, _ = g.setup(r1.to_dicts(), TOXIC)
+    key = gp.load_key(bf.binarify_proving_key(pk))
+    w2 = list(w)
+    w2[5] = R                                   # out of range, must not be silently reduced
+    with pytest.raises(_lib.ZkrError) as ei:
+        gp.prove(key, bf.binarify_witness(w2))
+    assert ei.value.code == -3
+    w3 = list(w)
+    w3[0] = 2                                   # witness[0] must be the constant 1
+    with pytest.raises(_lib.ZkrError) as ei:
+        gp.prove(key, bf.binarify_witness(w3))
+    assert ei.value.code == -3
+    with pytest.raises(_lib.ZkrError):          # wrong length
+        gp.prove(key, bf.binarify_witness(w[:-1]))
+    with pytest.raises(_lib.ZkrError) as ei:    # blinding scalar out of range
+        gp.prove(key, bf.binarify_witness(w), r=R)
+    assert ei.value.code == -3
+    # still healthy afterwards
+    got, _ = gp.prove(key, bf.binarify_witness(w), 3, 4)
+    assert got == g.proof_to_bytes(g.gen_proof(pk, w, 3, 4)[0])
+    # malformed keys
+    good = bf.binarify_proving_key(pk)
+    for bad in (good[:100], good[:-1], b"\xff" * 40 + good[40:]):
+        with pytest.raises(_lib.ZkrError) as ei:
+            gp.load_key(bad)
+        assert ei.value.code == -2
+
+
+def test_invalid_witness_matches_websnark_h(gp):
+    """websnark never reads polsC: for a witness violating A.B = C its H is still the upper half of A.B;
+    the GPU path must reproduce that (oracle calc_h_websnark), even though the proof will not verify."""
+    r1, w = synth.generate(60, 2, seed=5)
+    pk, vk, _ = g.setup(r1.to_dicts(), TOXIC)
+    key = gp.load_key(bf.binarify_proving_key(pk))
+    w2 = list(w)
+    w2[10] = (w2[10] + 12345) % R
+    got, _ = gp.prove(key, bf.binarify_witness(w2), 7, 9)
+    want, pub = g.gen_proof(pk, w2, 7, 9, h_method=g.calc_h_websnark)
+    assert got == g.proof_to_bytes(want)
+    assert not g.verify(vk, g.proof_from_bytes(got), pub)
+
+
+def test_gpu_setup_matches_oracle_setup(gp):
+    """zkr_synth_setup + host assembly == binarifyProvingKey(oracle setup) byte for byte; same vk."""
+    r1, w = synth.generate(120, 5, seed=6)
+    pk, vk, _ = g.setup(r1.to_dicts(), TOXIC)
+    pk_bin, vk_gpu = keygen.synth_setup(gp.ctx, r1, TOXIC)
+    ref = bf.binarify_proving_key(pk)
+    assert pk_bin.tobytes() == ref
+    assert pk_bin.tobytes() == binarify.binarifyProvingKey(bf.pk_to_json(pk))
+    for k in ("vk_alfa_1", "vk_beta_2", "vk_gamma_2", "vk_delta_2", "IC"):
+        assert vk_gpu[k] == vk[k], k
+
+
+def test_api_mirror(gp):
+    """createProofGenerator / genProof keep the reference's shapes (common.ts:40-51)."""
+    r1, w = synth.generate(30, 3, seed=7)
+    pk, vk, _ = g.setup(r1.to_dicts(), TOXIC)
+    pkj, vkj = bf.pk_to_json(pk), bf.vk_to_json(vk)
+
+    def calc(name, inputs):
+        assert name == "tx.circom"
+        return w, 3
+
+    def is_valid(vkey, proof, pub):
+        return g.verify(bf.vk_from_json(vkey), bf.proof_from_json(proof), [int(x) for x in pub])
+
+    gen = prover.createProofGenerator(pkj, vkj, "tx.circom", calc, is_valid, prover=gp)
+    out = gen({"any": 1})
+    assert set(out) == {"proof", "solidityProof"}
+    sp = out["solidityProof"]
+    assert len(sp["a"]) == 2 and len(sp["c"]) == 2 and len(sp["b"]) == 2 and len(sp["inputs"]) == 3
+    assert sp["b"][0] == list(reversed(out["proof"]["pi_b"][0]))
+    assert out["proof"]["pi_a"][2] == "1" and out["proof"]["pi_b"][2] == ["1", "0"]
+    res = prover.genProof(pkj, w, 0, 0, prover=gp)
+    assert res["publicSignals"] == [str(x) for x in w[1:4]]
+    want, _ = g.gen_proof(pk, w, 0, 0)
+    assert bf.proof_from_json(res["proof"]) == want
+    # a generator whose verifier says no raises like common.ts:36-38
+    gen_bad = prover.createProofGenerator(pkj, vkj, "tx.circom", calc, lambda *a: False, prover=gp)
+    with pytest.raises(RuntimeError, match="Invalid proof generated"):
+        gen_bad({})
+
+
+@pytest.mark.parametrize("shape", ["withdraw", "tx", "tx_2p20"])
+def test_prove_full_size(gp, shape):
+    """BASELINE configs[0..1] at full size: GPU setup -> prove -> toxic-waste exponent check (no MSM / NTT
+    code shared with the GPU path) -> pairing verification -> tamper-negative -> determinism."""
+    nc, npub = synth.SHAPES[shape]
+    t0 = time.time()
+    r1, w = synth.generate(nc, npub, seed=11)
+    pk_bin, vk = keygen.synth_setup(gp.ctx, r1, TOXIC)
+    key = gp.load_key(pk_bin)
+    m = gp.key_info(key)["domainSize"]
+    wbin = np.frombuffer(synth.witness_bytes(w), dtype=np.uint8)
+    rng = random.Random(5)
+    r, s = rng.randrange(R), rng.randrange(R)
+    got, stats = gp.prove(key, wbin, r, s)
+    again, _ = gp.prove(key, wbin, r, s)
+    assert got == again
+    print("\n%s: m=2^%d nVars=%d prove %.2f ms (setup+gen %.1f s) stats=%s" % (
+        shape, m.bit_length() - 1, r1.nVars, stats["total_ms"], time.time() - t0, stats))
+    proof = g.proof_from_bytes(got)
+    assert g.exponent_check_flat(r1.with_input_rows(), r1.pool, npub, w, TOXIC, m, proof, r, s)
+    pub = w[1:npub + 1]
+    assert g.verify(vk, proof, pub)
+    bad = list(pub)
+    bad[-1] = (bad[-1] + 1) % R
+    assert not g.verify(vk, proof, bad)
+    zero, _ = gp.prove(key, wbin, 0, 0)          # snarkjs debug mode
+    assert g.exponent_check_flat(r1.with_input_rows(), r1.pool, npub, w, TOXIC, m, g.proof_from_bytes(zero), 0, 0)
+    gp.L.zkr_pkey_free(key)
+    gp._keys.remove(key)
