@@ -81,6 +81,15 @@ int zkr_ctx_synchronize(zkr_ctx* ctx);
 /* number of this library's kernels launched through ctx since creation */
 uint64_t zkr_ctx_kernel_launches(const zkr_ctx* ctx);
 
+/* Per-kernel device timing (CUDA events on the launching stream) for roofline reporting.
+ * id: 0 = G1 bucket accumulation (k_accum_affine<Fq>), 1 = G2 bucket accumulation, 2 = NTT pass.
+ * units: work summed over the recorded launches -- mixed additions for ids 0/1, elements for id 2. */
+int zkr_ctx_set_profile(zkr_ctx* ctx, int on);
+/* on != 0: zkr_prove runs its stages back to back on the ctx stream instead of forking five streams
+ * (isolated per-kernel timings; the default overlaps the MSMs and the H pipeline). */
+int zkr_ctx_set_serial(zkr_ctx* ctx, int on);
+int zkr_ctx_profile_read(zkr_ctx* ctx, int id, double* total_ms, int* launches, double* units);
+
 /* plain device-memory helpers on ctx's GPU (stream-ordered on the ctx stream; download synchronises).
  * They let a host language without a CUDA binding stage "already resident" inputs. */
 int zkr_dev_malloc(zkr_ctx* ctx, size_t bytes, void** d_out);

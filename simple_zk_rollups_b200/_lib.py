@@ -40,6 +40,10 @@ _SIGS = {
     "zkr_ctx_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "zkr_ctx_synchronize": (C.c_int, [C.c_void_p]),
     "zkr_ctx_kernel_launches": (C.c_uint64, [C.c_void_p]),
+    "zkr_ctx_set_profile": (C.c_int, [C.c_void_p, C.c_int]),
+    "zkr_ctx_set_serial": (C.c_int, [C.c_void_p, C.c_int]),
+    "zkr_ctx_profile_read": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int),
+                                       C.POINTER(C.c_double)]),
     "zkr_dev_malloc": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
     "zkr_dev_free": (C.c_int, [C.c_void_p, C.c_void_p]),
     "zkr_dev_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),

@@ -46,6 +46,16 @@ struct DevBuf {
 
 constexpr int kNumStreams = 6;
 
+// Per-kernel device timing for bench.py's roofline: rings of CUDA event pairs recorded on the
+// launching stream around selected kernels while profiling is enabled.
+enum ProfId { PROF_ACCUM_G1 = 0, PROF_ACCUM_G2 = 1, PROF_NTT_PASS = 2, PROF_COUNT = 3 };
+constexpr int kProfRing = 512;
+struct ProfRing {
+    cudaEvent_t ev[2 * kProfRing] = {};
+    int n = 0;
+    double units = 0;     // caller-defined work units summed over the recorded launches
+};
+
 }  // namespace zkr
 
 struct zkr_ctx {
@@ -59,6 +69,12 @@ struct zkr_ctx {
     std::map<int, zkr::NttTables*> ntt;          // per log_n twiddle tables
     std::map<std::string, zkr::DevBuf> scratch;  // named, grow-only device scratch
     zkr_stats last_stats = {};
+    bool profiling = false;
+    bool serial = false;                         // run a proof's stages back to back on one stream
+    zkr::ProfRing prof[zkr::PROF_COUNT];
+    // returns the slot to pass to prof_end, or -1 when not recording
+    int prof_begin(int id, cudaStream_t st, double units);
+    void prof_end(int id, int slot, cudaStream_t st);
 
     // grow-only named scratch buffer on this ctx's device
     int scratch_get(const char* name, size_t bytes, void** out);

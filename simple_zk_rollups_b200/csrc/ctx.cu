@@ -92,6 +92,9 @@ extern "C" void zkr_ctx_destroy(zkr_ctx* c) {
         cudaEventDestroy(c->ev_join[i]);
     }
     cudaEventDestroy(c->ev_fork);
+    for (auto& r : c->prof)
+        for (auto& e : r.ev)
+            if (e) cudaEventDestroy(e);
     delete c;
 }
 
@@ -171,5 +174,56 @@ extern "C" int zkr_dev_download(zkr_ctx* c, void* h_dst, const void* d_src, size
     DeviceGuard g(c->device);
     ZKR_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, c->user_stream));
     ZKR_CUDA(cudaStreamSynchronize(c->user_stream));
+    return ZKR_OK;
+}
+
+int zkr_ctx::prof_begin(int id, cudaStream_t st, double units) {
+    if (!profiling) return -1;
+    zkr::ProfRing& r = prof[id];
+    if (r.n >= zkr::kProfRing) return -1;
+    const int slot = r.n++;
+    for (int k = 0; k < 2; k++)
+        if (!r.ev[2 * slot + k]) cudaEventCreate(&r.ev[2 * slot + k]);
+    r.units += units;
+    cudaEventRecord(r.ev[2 * slot], st);
+    return slot;
+}
+
+void zkr_ctx::prof_end(int id, int slot, cudaStream_t st) {
+    if (slot >= 0) cudaEventRecord(prof[id].ev[2 * slot + 1], st);
+}
+
+extern "C" int zkr_ctx_set_profile(zkr_ctx* c, int on) {
+    if (!c) return ZKR_E_INVALID;
+    DeviceGuard g(c->device);
+    ZKR_CUDA(cudaDeviceSynchronize());
+    c->profiling = on != 0;
+    for (auto& r : c->prof) {
+        r.n = 0;
+        r.units = 0;
+    }
+    return ZKR_OK;
+}
+
+extern "C" int zkr_ctx_set_serial(zkr_ctx* c, int on) {
+    if (!c) return ZKR_E_INVALID;
+    c->serial = on != 0;
+    return ZKR_OK;
+}
+
+extern "C" int zkr_ctx_profile_read(zkr_ctx* c, int id, double* total_ms, int* launches, double* units) {
+    if (!c || id < 0 || id >= PROF_COUNT) return ZKR_E_INVALID;
+    DeviceGuard g(c->device);
+    ZKR_CUDA(cudaDeviceSynchronize());
+    ProfRing& r = c->prof[id];
+    double tot = 0;
+    for (int i = 0; i < r.n; i++) {
+        float ms = 0;
+        ZKR_CUDA(cudaEventElapsedTime(&ms, r.ev[2 * i], r.ev[2 * i + 1]));
+        tot += ms;
+    }
+    if (total_ms) *total_ms = tot;
+    if (launches) *launches = r.n;
+    if (units) *units = r.units;
     return ZKR_OK;
 }

@@ -504,8 +504,10 @@ int msm_run(zkr_ctx* ctx, cudaStream_t st, const zkr_bases* b, const uint32_t* d
     const int L = 1 << b->logL;
     const size_t smem = (size_t)(kAccumThreads / 32) * 2 * 32 * (L + 1) * 4;
     XYZZ<F>* buckets = (XYZZ<F>*)wk.buckets;
+    const int pslot = ctx->prof_begin(sizeof(F) == 32 ? PROF_ACCUM_G1 : PROF_ACCUM_G2, st, (double)total);
     ZKR_LAUNCH(ctx, (k_accum_affine<F, kPrefetch>), b->T1p / kAccumThreads, kAccumThreads, smem, st, dk.Current(),
                dv.Current(), total, b->logL, b->table, buckets, (XYZZ<F>*)wk.bnd[0], wk.bnd_keys[0], nb);
+    ctx->prof_end(sizeof(F) == 32 ? PROF_ACCUM_G1 : PROF_ACCUM_G2, pslot, st);
     // boundary levels
     size_t cnt = 2 * (size_t)b->T1p;
     int cur = 0;

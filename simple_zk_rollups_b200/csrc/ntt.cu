@@ -374,10 +374,12 @@ int ntt_run(zkr_ctx* ctx, cudaStream_t st, Fr* data, int log_n, bool dit, bool i
         const size_t smem = (size_t)8 * (tile + (tile >> 3) + 4) * sizeof(uint32_t);
         const unsigned blocks = 1u << (log_n - T);
         // sub-NTT root: omega_{2^k} = W-table stride 2^(kw-k); the table is indexed in units of omega_{2^kw}
+        const int pslot = ctx->prof_begin(PROF_NTT_PASS, st, (double)((size_t)1 << log_n));
         if (dit) ZKR_LAUNCH(ctx, k_ntt_pass<true>, blocks, threads, smem, st, data, k, c, s, chunk_log, W, t->kw,
                             tlo, thi, t->lb, log_n - chunk_log);
         else ZKR_LAUNCH(ctx, k_ntt_pass<false>, blocks, threads, smem, st, data, k, c, s, chunk_log, W, t->kw,
                         tlo, thi, t->lb, log_n - chunk_log);
+        ctx->prof_end(PROF_NTT_PASS, pslot, st);
     }
     return ZKR_OK;
 }

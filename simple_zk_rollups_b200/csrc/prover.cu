@@ -356,8 +356,10 @@ static int prove_enqueue(zkr_ctx* ctx, const zkr_pkey* pk, char* d_proof, bool t
     cudaEvent_t const* ev = pk->ev;
     ZKR_LAUNCH(ctx, k_prep_scalars, 1, 1, 0, us, pk->wext, n, (const Fr*)pk->rs_dev, pk->err);
     ZKR_LAUNCH(ctx, k_witness_range, ceil_div(n, 256), 256, 0, us, pk->wext, n, pk->err);
-    ZKR_TRY(ctx->fork(5));
-    cudaStream_t sH = ctx->s[0], sA = ctx->s[1], sB1 = ctx->s[2], sB2 = ctx->s[3], sC = ctx->s[4];
+    const bool par = !ctx->serial;
+    if (par) ZKR_TRY(ctx->fork(5));
+    cudaStream_t sH = par ? ctx->s[0] : us, sA = par ? ctx->s[1] : us, sB1 = par ? ctx->s[2] : us,
+                 sB2 = par ? ctx->s[3] : us, sC = par ? ctx->s[4] : us;
     const uint32_t* w = (const uint32_t*)pk->wext;
     // heaviest first: the G2 MSM costs ~3 G1 MSMs
     if (timed) cudaEventRecord(ev[6], sB2);
@@ -383,10 +385,12 @@ static int prove_enqueue(zkr_ctx* ctx, const zkr_pkey* pk, char* d_proof, bool t
     ZKR_TRY(msm_run_g1(ctx, sC, pk->C, w, pk->res + R_C));
     if (timed) cudaEventRecord(ev[11], sC);
     // the two blinding scalar multiplications need A and B1
-    ZKR_CUDA(cudaEventRecord(ctx->ev_join[2], sB1));
-    ZKR_CUDA(cudaStreamWaitEvent(sA, ctx->ev_join[2], 0));
+    if (par) {
+        ZKR_CUDA(cudaEventRecord(ctx->ev_join[2], sB1));
+        ZKR_CUDA(cudaStreamWaitEvent(sA, ctx->ev_join[2], 0));
+    }
     ZKR_LAUNCH(ctx, k_blind_muls, 2, 1, 0, sA, pk->res, pk->wext, n);
-    ZKR_TRY(ctx->join(5));
+    if (par) ZKR_TRY(ctx->join(5));
     if (timed) cudaEventRecord(ev[12], us);
     ZKR_LAUNCH(ctx, k_finish, 3, 1, 0, us, (const char*)pk->res, d_proof);
     if (timed) cudaEventRecord(ev[13], us);
