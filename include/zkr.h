@@ -181,6 +181,11 @@ typedef struct zkr_r1cs_csc {
 int zkr_synth_setup(zkr_ctx* ctx, const zkr_r1cs_csc* r1cs, const void* toxic, void* out_a, void* out_b1,
                     void* out_b2, void* out_c, void* out_h, void* out_vk);
 
+/* points[i] = scalars[i] * G (group 1: G1 generator (1,2); group 2: the G2 generator of TxVerifier.sol:30-35);
+ * scalars n x 32 B std form, out n x 64 / 128 B affine Fq-M; host buffers.  Workload generator for the
+ * standalone MSM sweeps (BASELINE.json configs[2]). */
+int zkr_synth_points(zkr_ctx* ctx, int group, const void* scalars, size_t n, void* out_points);
+
 /* ---- test hooks (element-wise field / curve kernels; used by the parity tests) --------- */
 /* field: 0 = Fq, 1 = Fr.  op: 0 mul, 1 add, 2 sub, 3 sqr, 4 inverse, 5 to_mont, 6 from_mont.
  * a, b, out: n x 32 B host buffers (Montgomery form operands for mul/add/sub/sqr/inverse). */

@@ -229,6 +229,71 @@ k_accum_xyzz(const uint32_t* __restrict__ in_keys, const XYZZ<F>* __restrict__ i
     }
 }
 
+// all remaining boundary levels in ONE launch (single CTA): used once the list is short enough that
+// launch latency, not work, dominates.  Buffers ping-pong in global memory; __syncthreads orders them.
+constexpr int kFinishThreads = 256;
+constexpr uint32_t kFinishMax = kFinishThreads << kLevelLog;      // 4096 entries
+template <class F>
+__global__ void __launch_bounds__(kFinishThreads)
+k_accum_finish(uint32_t* keys_a, XYZZ<F>* pts_a, uint32_t* keys_b, XYZZ<F>* pts_b, uint32_t count,
+               XYZZ<F>* __restrict__ buckets, uint32_t sentinel) {
+    const uint32_t t = threadIdx.x;
+    uint32_t* in_keys = keys_a;
+    XYZZ<F>* in_pts = pts_a;
+    uint32_t* out_keys = keys_b;
+    XYZZ<F>* out_pts = pts_b;
+    for (;;) {
+        const bool final_level = count <= (1u << kLevelLog);
+        const uint32_t T = (count + (1u << kLevelLog) - 1) >> kLevelLog;
+        if (t < T) {
+            const uint32_t begin = t << kLevelLog;
+            uint32_t end = begin + (1u << kLevelLog);
+            if (end > count) end = count;
+            XYZZ<F> acc = XYZZ<F>::identity();
+            uint32_t cur = sentinel, head_key = sentinel, tail_key = sentinel;
+            bool first_run = true;
+#pragma unroll 1
+            for (uint32_t e = begin; e < end; e++) {
+                const uint32_t key = in_keys[e];
+                if (key >= sentinel) continue;
+                if (cur == sentinel) cur = key;
+                if (key != cur) {
+                    if (first_run && !final_level) {
+                        acc.store(out_pts + 2 * t);
+                        head_key = cur;
+                    } else {
+                        acc.store(buckets + cur);
+                    }
+                    first_run = false;
+                    acc = XYZZ<F>::identity();
+                    cur = key;
+                }
+                acc.add(XYZZ<F>::load(in_pts + e));
+            }
+            if (cur < sentinel) {
+                if (final_level) {
+                    acc.store(buckets + cur);
+                } else if (first_run) {
+                    acc.store(out_pts + 2 * t);
+                    head_key = cur;
+                } else {
+                    acc.store(out_pts + 2 * t + 1);
+                    tail_key = cur;
+                }
+            }
+            if (!final_level) {
+                out_keys[2 * t] = head_key;
+                out_keys[2 * t + 1] = tail_key;
+            }
+        }
+        if (final_level) break;
+        __syncthreads();
+        count = 2 * T;
+        uint32_t* tk = in_keys; in_keys = out_keys; out_keys = tk;
+        XYZZ<F>* tp = in_pts; in_pts = out_pts; out_pts = tp;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // block-wide helpers on XYZZ points staged in shared memory (blockDim.x == NT, power of two).
 // All point arithmetic goes through the memory-to-memory helpers of ec.cuh.
@@ -455,7 +520,8 @@ int bases_build(zkr_ctx* ctx, zkr_bases* b, const char* h_points, size_t n_src, 
     ZKR_CUDA(cudaMalloc(&wk.buckets, XB * (size_t)b->plan.nbuckets));
     const size_t bnd0 = 2 * (size_t)b->T1p;
     const size_t lvl = (size_t)1 << kLevelLog;
-    const size_t bnd1 = 2 * (((bnd0 + lvl - 1) / lvl + 63) / 64 * 64);
+    size_t bnd1 = 2 * (((bnd0 + lvl - 1) / lvl + 63) / 64 * 64);
+    if (bnd1 < 2 * (size_t)kFinishThreads) bnd1 = 2 * (size_t)kFinishThreads;
     ZKR_CUDA(cudaMalloc(&wk.bnd[0], XB * bnd0));
     ZKR_CUDA(cudaMalloc(&wk.bnd[1], XB * bnd1));
     ZKR_CUDA(cudaMalloc(&wk.bnd_keys[0], 4 * bnd0));
@@ -513,6 +579,11 @@ int msm_run(zkr_ctx* ctx, cudaStream_t st, const zkr_bases* b, const uint32_t* d
     int cur = 0;
     const size_t lvl = (size_t)1 << kLevelLog;
     for (;;) {
+        if (cnt <= kFinishMax) {
+            ZKR_LAUNCH(ctx, k_accum_finish<F>, 1, kFinishThreads, 0, st, wk.bnd_keys[cur], (XYZZ<F>*)wk.bnd[cur],
+                       wk.bnd_keys[cur ^ 1], (XYZZ<F>*)wk.bnd[cur ^ 1], (uint32_t)cnt, buckets, nb);
+            break;
+        }
         const bool fin = cnt <= lvl;
         const size_t T = (cnt + lvl - 1) / lvl;
         const unsigned blocks = (unsigned)((T + 63) / 64);
@@ -523,6 +594,9 @@ int msm_run(zkr_ctx* ctx, cudaStream_t st, const zkr_bases* b, const uint32_t* d
         cur ^= 1;
     }
     // bucket reduction
+    // 16 buckets per thread: the block-level scan costs ~2600 point additions per CTA, so CTAs are kept few
+    // (total work stays ~1.3x the running sums and hides behind the other MSMs' bulk kernels); measured:
+    // one bucket per thread (256 CTAs) is no faster in isolation and 2 ms slower per overlapped proof.
     uint32_t G = nb / (kReduceThreads * 16);
     if (G < 1) G = 1;
     if (G > 128) G = 128;

@@ -76,7 +76,7 @@ __global__ void k_pow_table(Fr* out, unsigned count, const Fr* base, unsigned lo
 __device__ __forceinline__ int slot_of(int e) { return e + (e >> 3); }
 
 template <bool DIT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 k_ntt_pass(Fr* __restrict__ data, int k, int c, int s, int chunk_log, const Fr* __restrict__ W, int kw,
            const Fr* __restrict__ tlo, const Fr* __restrict__ thi, int lb, int tw_shift) {
     extern __shared__ uint32_t sm[];

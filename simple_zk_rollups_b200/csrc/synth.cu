@@ -269,3 +269,27 @@ extern "C" int zkr_synth_setup(zkr_ctx* ctx, const zkr_r1cs_csc* r, const void* 
     for (void* p : fr) cudaFree(p);
     return ZKR_OK;
 }
+
+// points[i] = scalars[i] * G  (G1 or G2 generator), affine Fq-M, binarify encoding; host buffers.
+extern "C" int zkr_synth_points(zkr_ctx* ctx, int group, const void* scalars, size_t n, void* out_points) {
+    if (!ctx || !scalars || !out_points || (group != 1 && group != 2) || n == 0 || n > 0xffffffffull) return ZKR_E_INVALID;
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = ctx->s[0];
+    Fr* d_sc;
+    ZKR_CUDA(cudaMalloc(&d_sc, 32 * n));
+    ZKR_CUDA(cudaMemcpyAsync(d_sc, scalars, 32 * n, cudaMemcpyHostToDevice, st));
+    int rc;
+    if (group == 1) {
+        G1Affine* t;
+        ZKR_TRY(build_table<Fq>(ctx, st, &t));
+        rc = fixed_base<Fq>(ctx, st, t, d_sc, (uint32_t)n, out_points);
+        cudaFree(t);
+    } else {
+        G2Affine* t;
+        ZKR_TRY(build_table<Fq2>(ctx, st, &t));
+        rc = fixed_base<Fq2>(ctx, st, t, d_sc, (uint32_t)n, out_points);
+        cudaFree(t);
+    }
+    cudaFree(d_sc);
+    return rc;
+}
