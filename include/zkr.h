@@ -198,7 +198,8 @@ int zkr_test_curve_op(zkr_ctx* ctx, int group, int op, const void* p, const void
  * 5 buckets, 6 result, 7 reduce partials, 8/9 boundary keys, 10/11 boundary partials). */
 int zkr_test_bases_peek(const zkr_bases* b, int what, size_t offset, void* out, size_t bytes);
 /* integer-pipe microbenchmarks: which: 0 = IMAD chain, 1 = IMAD.WIDE chain, 2 = Fq modmul chain,
- * 3 = XYZZ mixed-add chain.  Returns operations per second (IMADs / modmuls / madds) in *ops_per_s. */
+ * 3 = XYZZ mixed-add chain, 4 = DFMA chain (FP64 pipe), 5 = DFMA + IMAD.WIDE pairs, 6 = DFMA + 64-bit
+ * add pairs, 7 = 64-bit add chain.  Returns operations per second (IMADs / modmuls / madds / pairs). */
 int zkr_microbench(zkr_ctx* ctx, int which, int iters, double* ops_per_s, float* ms);
 
 #ifdef __cplusplus

@@ -75,27 +75,34 @@ __global__ void k_pow_table(Fr* out, unsigned count, const Fr* base, unsigned lo
 
 __device__ __forceinline__ int slot_of(int e) { return e + (e >> 3); }
 
-template <bool DIT>
+// MODE selects where the tile is written back (the multi-GPU four-step exchange is fused into the pass):
+//   0  in place (single GPU, and the local passes of a sharded transform)
+//   1  push to the peers' ROWS buffers: row i of the first DIF pass belongs to rank i >> (k - g)
+//   2  push to the peers' COLS buffers: column j of the last-but-one DIT pass belongs to rank j >> (s0 - g)
+// ls = log2 of the row stride in memory (== s except for a COLS slab, where it is s0 - g) and ctw = global
+// column of this rank's first local column (twiddles use global coordinates).
+template <bool DIT, int MODE>
 __global__ void __launch_bounds__(256, 2)
-k_ntt_pass(Fr* __restrict__ data, int k, int c, int s, int chunk_log, const Fr* __restrict__ W, int kw,
-           const Fr* __restrict__ tlo, const Fr* __restrict__ thi, int lb, int tw_shift) {
+k_ntt_pass(Fr* __restrict__ data, int k, int c, int s, int ls, int chunk_log, unsigned ctw, const Fr* __restrict__ W,
+           int kw, const Fr* __restrict__ tlo, const Fr* __restrict__ thi, int lb, int tw_shift, NttXchg xp) {
     extern __shared__ uint32_t sm[];
     const int T = k + c;
     const int tile = 1 << T;
     const int plane = tile + (tile >> 3) + 4;
     const int tid = threadIdx.x;
-    const unsigned cgmask = (1u << (s - c)) - 1;
+    const unsigned cgmask = (1u << (ls - c)) - 1;
     const unsigned cg = blockIdx.x & cgmask;
-    const size_t q = blockIdx.x >> (s - c);
+    const size_t q = blockIdx.x >> (ls - c);
     Fr* chunk = data + (q << chunk_log);
-    const unsigned c0 = cg << c;
+    const unsigned cm = cg << c;             // first column of the tile in memory
+    const unsigned c0 = ctw + cm;            // ... and in the transform's global coordinates
     const int cmask = (1 << c) - 1;
 
     // ---- global -> shared, 16-byte units
     for (int u = tid; u < 2 * tile; u += blockDim.x) {
         int e = u >> 1, half = u & 1;
         int row = e >> c, col = e & cmask;
-        const uint4* src = reinterpret_cast<const uint4*>(chunk + ((size_t)row << s) + c0 + col) + half;
+        const uint4* src = reinterpret_cast<const uint4*>(chunk + ((size_t)row << ls) + cm + col) + half;
         uint4 v = *src;
         uint32_t* d = sm + (4 * half) * plane + slot_of(e);
         d[0] = v.x;
@@ -198,8 +205,19 @@ k_ntt_pass(Fr* __restrict__ data, int k, int c, int s, int chunk_log, const Fr* 
         int row = e >> c, col = e & cmask;
         const uint32_t* d = sm + (4 * half) * plane + slot_of(e);
         uint4 v = make_uint4(d[0], d[plane], d[2 * plane], d[3 * plane]);
-        uint4* dst = reinterpret_cast<uint4*>(chunk + ((size_t)row << s) + c0 + col) + half;
-        *dst = v;
+        Fr* dp;
+        if (MODE == 0) {
+            dp = chunk + ((size_t)row << ls) + cm + col;
+        } else if (MODE == 1) {
+            const int rl = k - xp.g;         // log2 rows per rank
+            dp = xp.peer[row >> rl] + ((size_t)(row & ((1 << rl) - 1)) << xp.s0) + c0 + col;
+        } else {
+            const unsigned j = ((unsigned)row << s) + cm + col;                 // column inside row-chunk q
+            const int cl = xp.s0 - xp.g;     // log2 columns per rank
+            const size_t i = ((size_t)xp.rank << (xp.k0 - xp.g)) + q;           // global row
+            dp = xp.peer[j >> cl] + (i << cl) + (j & ((1u << cl) - 1));
+        }
+        *(reinterpret_cast<uint4*>(dp) + half) = v;
     }
 }
 
@@ -310,8 +328,10 @@ int ntt_get_tables(zkr_ctx* ctx, int log_n, NttTables** out) {
     }
     static bool attr_done = false;
     if (!attr_done) {
-        ZKR_CUDA(cudaFuncSetAttribute(k_ntt_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        ZKR_CUDA(cudaFuncSetAttribute(k_ntt_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        ZKR_CUDA(cudaFuncSetAttribute((k_ntt_pass<false, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        ZKR_CUDA(cudaFuncSetAttribute((k_ntt_pass<true, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        ZKR_CUDA(cudaFuncSetAttribute((k_ntt_pass<false, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        ZKR_CUDA(cudaFuncSetAttribute((k_ntt_pass<true, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         attr_done = true;
     }
     NttTables* t = new NttTables();

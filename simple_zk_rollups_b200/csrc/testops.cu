@@ -111,6 +111,89 @@ __global__ void k_bench_madd(uint32_t* out, int iters) {
     if (acc.x.v[0] == 0x12345678u && acc.zz.v[7] == 1) out[0] = acc.y.v[3];
 }
 
+// FP64 pipe probes (B200 keeps the full-rate FP64 unit): can DFMA carry part of the limb products?
+__global__ void k_bench_dfma(uint32_t* out, int iters, double a, double b) {
+    double x[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) x[j] = (double)(threadIdx.x + j);
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) asm volatile("fma.rz.f64 %0, %0, %1, %2;" : "+d"(x[j]) : "d"(a), "d"(b));
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) s += x[j];
+    if (s == 0.12345678) out[0] = 1;
+}
+
+// 16 DFMA + 16 IMAD.WIDE per inner iteration, interleaved: do the two pipes overlap?
+__global__ void k_bench_dfma_imadw(uint32_t* out, int iters, double a, double b, uint32_t m) {
+    double x[8];
+    unsigned long long y[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) { x[j] = (double)(threadIdx.x + j); y[j] = threadIdx.x + j; }
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                asm volatile("fma.rz.f64 %0, %0, %1, %2;" : "+d"(x[j]) : "d"(a), "d"(b));
+                uint32_t lo = (uint32_t)y[j];
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(y[j]) : "r"(lo), "r"(m));
+            }
+        }
+    }
+    double s = 0;
+    unsigned long long t = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) { s += x[j]; t ^= y[j]; }
+    if (s == 0.12345678 && t == 5) out[0] = 1;
+}
+
+// 16 DFMA + 16 64-bit integer adds (2 x IADD3 with carry) per inner iteration: Emmart-style accumulation mix
+__global__ void k_bench_dfma_iadd(uint32_t* out, int iters, double a, double b) {
+    double x[8];
+    unsigned long long y[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) { x[j] = (double)(threadIdx.x + j); y[j] = threadIdx.x + j; }
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                asm volatile("fma.rz.f64 %0, %0, %1, %2;" : "+d"(x[j]) : "d"(a), "d"(b));
+                y[j] += (unsigned long long)__double_as_longlong(x[(j + 4) & 7]);
+            }
+        }
+    }
+    double s = 0;
+    unsigned long long t = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) { s += x[j]; t ^= y[j]; }
+    if (s == 0.12345678 && t == 5) out[0] = 1;
+}
+
+// plain 64-bit add chains (alu pipe): IADD3 + IADD3.X rate
+__global__ void k_bench_iadd64(uint32_t* out, int iters, unsigned long long a) {
+    unsigned long long y[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) y[j] = threadIdx.x + j;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) asm volatile("add.u64 %0, %0, %1;" : "+l"(y[j]) : "l"(a + j));
+        }
+    }
+    unsigned long long t = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) t ^= y[j];
+    if (t == 5) out[0] = 1;
+}
+
 }  // namespace
 
 extern "C" int zkr_test_field_op(zkr_ctx* ctx, int field, int op, const void* a, const void* b, void* out, size_t n) {
@@ -162,7 +245,7 @@ extern "C" int zkr_test_curve_op(zkr_ctx* ctx, int group, int op, const void* p,
 }
 
 extern "C" int zkr_microbench(zkr_ctx* ctx, int which, int iters, double* ops_per_s, float* ms_out) {
-    if (!ctx || which < 0 || which > 3 || iters <= 0 || !ops_per_s) return ZKR_E_INVALID;
+    if (!ctx || which < 0 || which > 7 || iters <= 0 || !ops_per_s) return ZKR_E_INVALID;
     DeviceGuard g(ctx->device);
     uint32_t* dout = nullptr;
     ZKR_CUDA(cudaMalloc(&dout, 64));
@@ -182,8 +265,16 @@ extern "C" int zkr_microbench(zkr_ctx* ctx, int which, int iters, double* ops_pe
                 per_thread = 32.0 * iters; break;
             case 2: ZKR_LAUNCH(ctx, k_bench_modmul, blocks, threads, 0, ctx->s[0], dout, iters);
                 per_thread = 2.0 * iters; break;
-            default: ZKR_LAUNCH(ctx, k_bench_madd, blocks, threads, 0, ctx->s[0], dout, iters);
+            case 3: ZKR_LAUNCH(ctx, k_bench_madd, blocks, threads, 0, ctx->s[0], dout, iters);
                 per_thread = 1.0 * iters; break;
+            case 4: ZKR_LAUNCH(ctx, k_bench_dfma, blocks, threads, 0, ctx->s[0], dout, iters, 1.0000001, 0.5);
+                per_thread = 32.0 * iters; break;
+            case 5: ZKR_LAUNCH(ctx, k_bench_dfma_imadw, blocks, threads, 0, ctx->s[0], dout, iters, 1.0000001, 0.5, 0x9e3779b9u);
+                per_thread = 16.0 * iters; break;          // pairs (1 DFMA + 1 IMAD.WIDE)
+            case 6: ZKR_LAUNCH(ctx, k_bench_dfma_iadd, blocks, threads, 0, ctx->s[0], dout, iters, 1.0000001, 0.5);
+                per_thread = 16.0 * iters; break;          // pairs (1 DFMA + 1 64-bit add)
+            default: ZKR_LAUNCH(ctx, k_bench_iadd64, blocks, threads, 0, ctx->s[0], dout, iters, 0x123456789abcdefull);
+                per_thread = 32.0 * iters; break;
         }
         ZKR_CUDA(cudaEventRecord(e1, ctx->s[0]));
         ZKR_CUDA(cudaEventSynchronize(e1));

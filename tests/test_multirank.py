@@ -28,7 +28,7 @@ WORKER = textwrap.dedent("""
     assert cnt.item() == n_proofs                            # every proof is owned by exactly one rank
     dist.barrier()
     dist.destroy_process_group()
-    print("rank", rank, "ok")
+    sys.stdout.write("rank " + str(rank) + " ok\\n"); sys.stdout.flush()
 """) % ROOT
 
 

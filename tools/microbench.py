@@ -14,7 +14,9 @@ h = C.c_void_p()
 _lib.check(L.zkr_ctx_create(0, C.byref(h)))
 res = {}
 for name, which, iters in (("imad_per_s", 0, 100000), ("imad_wide_per_s", 1, 100000),
-                           ("fq_modmul_per_s", 2, 20000), ("g1_madd_per_s", 3, 3000)):
+                           ("fq_modmul_per_s", 2, 20000), ("g1_madd_per_s", 3, 3000),
+                           ("dfma_per_s", 4, 100000), ("dfma_imadw_pairs_per_s", 5, 100000),
+                           ("dfma_iadd64_pairs_per_s", 6, 100000), ("iadd64_per_s", 7, 100000)):
     ops, ms = C.c_double(), C.c_float()
     _lib.check(L.zkr_microbench(h, which, iters, C.byref(ops), C.byref(ms)))
     res[name] = ops.value
