@@ -161,6 +161,61 @@ int zkr_ntt(zkr_ctx* ctx, void* data, int log_n, int mode, int on_device);
  * BIT-REVERSED order when bitrev_out != 0 (what the prover feeds to the hExps MSM) or natural order. */
 int zkr_h_from_evals_dev(zkr_ctx* ctx, void* d_a_t, void* d_b_t, int log_m, void* d_h_out, int bitrev_out);
 
+/* ---- multi-GPU: peer-memory communicator, sharded MSM, sharded four-step NTT ----------------
+ * One zkr_comm per rank (GPU).  Each rank owns a device slab (flags | gather slots | two exchange
+ * buffers of max_elems_per_rank Fr elements) that every peer maps, so kernels store directly into
+ * peers' HBM over NVLink; there is no NCCL on the data path.  Wiring, across processes:
+ *     zkr_comm_create -> zkr_comm_export (64 B handle) -> exchange the handles by any means
+ *     (torch.distributed / MPI / a file) -> zkr_comm_connect(all handles, rank order);
+ * inside one process (one ctx per GPU): zkr_comm_connect_local.  world = 1, 2, 4 or 8.
+ * Replaces the web-worker fan-out of websnark's multiexp / fft inside groth16GenProof
+ * (operator/src/snarks/common.ts:29) by a fan-out over the GPUs of one NVSwitch box. */
+typedef struct zkr_comm zkr_comm;
+#define ZKR_IPC_HANDLE_BYTES 64
+int zkr_comm_create(zkr_ctx* ctx, int rank, int world, size_t max_elems_per_rank, zkr_comm** out);
+int zkr_comm_export(const zkr_comm* c, void* handle64);
+int zkr_comm_connect(zkr_comm* c, const void* handles /* world x 64 B, rank order */);
+int zkr_comm_connect_local(zkr_comm* const* comms, int world);
+/* device-side flag barrier across the ranks, ordered on the ctx stream (bounded spin: a missing peer
+ * turns into ZKR_E_NCCL at the next zkr_comm_check / synchronising call, not a hang) */
+int zkr_comm_barrier(zkr_comm* c);
+int zkr_comm_check(zkr_comm* c);
+/* device pointer of this rank's exchange buffer 0 / 1 */
+void* zkr_comm_buffer(zkr_comm* c, int which);
+int zkr_comm_info(const zkr_comm* c, int* rank, int* world, uint64_t* elems_per_buffer);
+void zkr_comm_destroy(zkr_comm* c);
+
+/* MSM sharded by point range: `b` holds THIS rank's contiguous slice of the points (zkr_bases_load on
+ * the slice), scalars the matching slice.  Each rank reduces its slice to one XYZZ point, stores it into
+ * every peer's gather slot, and all ranks add the `world` partials: out_affine (as zkr_msm) is the
+ * full sum on every rank. */
+int zkr_msm_sharded(zkr_comm* c, const zkr_bases* b, const void* scalars, size_t n_local,
+                    int scalars_on_device, void* out_affine);
+
+/* One proof over `world` GPUs (latency split).  zkr_pkey_load_bin_sharded keeps only rank's contiguous point
+ * range of each of the five base sets (A, B1, B2, C, hExps; blinding bases included) resident; every rank
+ * receives the full witness, computes A_T/B_T and h (replicated: at rollup sizes the H pipeline is a few ms
+ * and its exchange would cost more than it saves), runs its share of the five MSMs, stores the five partial
+ * sums into every peer's gather slot and assembles the proof.  All ranks return the same 256 bytes, identical
+ * to zkr_prove on one GPU.  Same arguments and error behaviour as zkr_prove. */
+int zkr_pkey_load_bin_sharded(zkr_ctx* ctx, const void* buf, size_t len, int rank, int world, zkr_pkey** out);
+int zkr_prove_sharded(zkr_comm* c, const zkr_pkey* pk, const void* witness, size_t n_signals,
+                      const void* r32, const void* s32, void* out_proof, zkr_stats* stats);
+
+/* Four-step NTT of 2^log_n elements sharded over the ranks, one all-to-all, fused into the pass that
+ * precedes it (remote stores).  View the index as (row i, column j), i < 2^k0, j < 2^s0, k0 =
+ * zkr_ntt_sharded_rows_log(log_n, world), s0 = log_n - k0, C = 2^s0:
+ *   COLS slab of rank p: all rows, columns [p C/world, (p+1) C/world): local[i * C/world + jl] = x[i C + p C/world + jl]
+ *   ROWS slab of rank q: the contiguous slice [q N/world, (q+1) N/world)
+ * mode = ZKR_NTT_{FORWARD,INVERSE,COSET_FORWARD,COSET_INVERSE} | exactly one of
+ *   ZKR_NTT_BITREV_OUT: input natural order in COLS slabs  -> output bit-reversed order in ROWS slabs
+ *   ZKR_NTT_BITREV_IN : input bit-reversed order in ROWS slabs -> output natural order in COLS slabs
+ * so transforms chain (DIF^-1 -> DIT -> DIF^-1, as the H pipeline does) with no extra exchange.
+ * Input: this rank's slab in exchange buffer src_buf; output: exchange buffer 1 - src_buf.
+ * Asynchronous, ordered on the ctx stream. */
+int zkr_ntt_sharded_rows_log(int log_n, int world);
+int zkr_ntt_sharded(zkr_comm* c, int log_n, int mode, int src_buf);
+
 /* ---- synthetic trusted setup (test / benchmark keys only) ------------------------------ */
 /* R1CS in CSC-by-signal form with coefficients taken from a pool:
  *   ptr_X[n_vars+1], row_X[nnz], cid_X[nnz] (u32), pool: n_pool x 32 B std form.

@@ -66,6 +66,21 @@ _SIGS = {
     "zkr_msm_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "zkr_ntt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "zkr_h_from_evals_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
+    "zkr_comm_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "zkr_comm_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "zkr_comm_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "zkr_comm_connect_local": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
+    "zkr_comm_barrier": (C.c_int, [C.c_void_p]),
+    "zkr_comm_check": (C.c_int, [C.c_void_p]),
+    "zkr_comm_buffer": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "zkr_comm_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint64)]),
+    "zkr_comm_destroy": (None, [C.c_void_p]),
+    "zkr_msm_sharded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "zkr_pkey_load_bin_sharded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "zkr_prove_sharded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.POINTER(Stats)]),
+    "zkr_ntt_sharded_rows_log": (C.c_int, [C.c_int, C.c_int]),
+    "zkr_ntt_sharded": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "zkr_synth_setup": (C.c_int, [C.c_void_p, C.POINTER(R1csCsc), C.c_void_p] + [C.c_void_p] * 6),
     "zkr_synth_points": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "zkr_test_field_op": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),

@@ -16,6 +16,8 @@
 //     the kernel; the prover chains DIF^-1 -> DIT -> DIF^-1 so no bit-reversal pass is ever run.
 //   * data may be in standard OR Montgomery form: every constant (twiddles, scalings) is stored in
 //     Montgomery form and mont_mul(x, cR) = x*c keeps the form of x.
+#include <cstdlib>
+
 #include "ntt_iface.cuh"
 
 namespace zkr {
@@ -77,15 +79,19 @@ __device__ __forceinline__ int slot_of(int e) { return e + (e >> 3); }
 
 // MODE selects where the tile is written back (the multi-GPU four-step exchange is fused into the pass):
 //   0  in place (single GPU, and the local passes of a sharded transform)
-//   1  push to the peers' ROWS buffers: row i of the first DIF pass belongs to rank i >> (k - g)
+//   1  COLS slab in, push to the peers' ROWS buffers: row i of the first DIF pass belongs to rank i >> (k - g)
 //   2  push to the peers' COLS buffers: column j of the last-but-one DIT pass belongs to rank j >> (s0 - g)
-// ls = log2 of the row stride in memory (== s except for a COLS slab, where it is s0 - g) and ctw = global
-// column of this rank's first local column (twiddles use global coordinates).
+//   3  in place on a COLS slab (last DIT pass)
+// On a COLS slab (modes 1, 3) ls_ = log2 of the row stride in memory (s0 - g) and ctw_ = global column of
+// this rank's first local column (twiddles use global coordinates); otherwise ls == s and ctw == 0.
 template <bool DIT, int MODE>
 __global__ void __launch_bounds__(256, 2)
-k_ntt_pass(Fr* __restrict__ data, int k, int c, int s, int ls, int chunk_log, unsigned ctw, const Fr* __restrict__ W,
+k_ntt_pass(Fr* __restrict__ data, int k, int c, int s, int ls_, int chunk_log, unsigned ctw_, const Fr* __restrict__ W,
            int kw, const Fr* __restrict__ tlo, const Fr* __restrict__ thi, int lb, int tw_shift, NttXchg xp) {
     extern __shared__ uint32_t sm[];
+    constexpr bool kSlab = MODE == 1 || MODE == 3;
+    const int ls = kSlab ? ls_ : s;
+    const unsigned ctw = kSlab ? ctw_ : 0u;
     const int T = k + c;
     const int tile = 1 << T;
     const int plane = tile + (tile >> 3) + 4;
@@ -206,7 +212,7 @@ k_ntt_pass(Fr* __restrict__ data, int k, int c, int s, int ls, int chunk_log, un
         const uint32_t* d = sm + (4 * half) * plane + slot_of(e);
         uint4 v = make_uint4(d[0], d[plane], d[2 * plane], d[3 * plane]);
         Fr* dp;
-        if (MODE == 0) {
+        if (MODE == 0 || MODE == 3) {
             dp = chunk + ((size_t)row << ls) + cm + col;
         } else if (MODE == 1) {
             const int rl = k - xp.g;         // log2 rows per rank
@@ -256,6 +262,23 @@ __global__ void k_scale_pow(Fr* x, size_t n, int log_n, const Fr* lo, const Fr* 
     size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     unsigned j = bitrev_idx ? (__brev((unsigned)p) >> (32 - log_n)) : (unsigned)p;
+    Fr t = Fr::load_ro(lo + (j & ((1u << lb) - 1))) * Fr::load_ro(hi + (j >> lb));
+    (Fr::load(x + p) * t).store(x + p);
+}
+
+// sharded variant: j = transform index of local element p of a COLS (natural) or ROWS (bit-reversed) slab
+__global__ void k_scale_pow_sharded(Fr* x, size_t n_local, int log_n, const Fr* lo, const Fr* hi, int lb, int layout,
+                                    int s0, int g, int rank) {
+    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_local) return;
+    unsigned j;
+    if (layout == 0) {
+        const int cl = s0 - g;
+        j = (unsigned)(((p >> cl) << s0) + ((size_t)rank << cl) + (p & (((size_t)1 << cl) - 1)));
+    } else {
+        const unsigned pos = (unsigned)(((size_t)rank << (log_n - g)) + p);
+        j = __brev(pos) >> (32 - log_n);
+    }
     Fr t = Fr::load_ro(lo + (j & ((1u << lb) - 1))) * Fr::load_ro(hi + (j >> lb));
     (Fr::load(x + p) * t).store(x + p);
 }
@@ -332,6 +355,7 @@ int ntt_get_tables(zkr_ctx* ctx, int log_n, NttTables** out) {
         ZKR_CUDA(cudaFuncSetAttribute((k_ntt_pass<true, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         ZKR_CUDA(cudaFuncSetAttribute((k_ntt_pass<false, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         ZKR_CUDA(cudaFuncSetAttribute((k_ntt_pass<true, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        ZKR_CUDA(cudaFuncSetAttribute((k_ntt_pass<true, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         attr_done = true;
     }
     NttTables* t = new NttTables();
@@ -364,6 +388,30 @@ int ntt_get_tables(zkr_ctx* ctx, int log_n, NttTables** out) {
     return ZKR_OK;
 }
 
+// one pass = one launch
+struct PassGeom {
+    int k, c, s, ls, chunk_log, tw_shift;
+    unsigned ctw, blocks;
+};
+
+template <int MODE>
+static int launch_pass(zkr_ctx* ctx, cudaStream_t st, const NttTables* t, Fr* data, const PassGeom& g, bool dit,
+                       bool inverse, const NttXchg& xp, double prof_units) {
+    const Fr* W = inverse ? t->wsub_i : t->wsub_f;
+    const Fr* tlo = inverse ? t->tw_lo_i : t->tw_lo_f;
+    const Fr* thi = inverse ? t->tw_hi_i : t->tw_hi_f;
+    const int tile = 1 << (g.k + g.c);
+    const int threads = tile / 8;
+    const size_t smem = (size_t)8 * (tile + (tile >> 3) + 4) * sizeof(uint32_t);
+    const int pslot = ctx->prof_begin(PROF_NTT_PASS, st, prof_units);
+    if (dit) ZKR_LAUNCH(ctx, (k_ntt_pass<true, MODE == 1 ? 3 : MODE>), g.blocks, threads, smem, st, data, g.k, g.c, g.s,
+                        g.ls, g.chunk_log, g.ctw, W, t->kw, tlo, thi, t->lb, g.tw_shift, xp);
+    else ZKR_LAUNCH(ctx, (k_ntt_pass<false, (MODE == 2 || MODE == 3) ? 0 : MODE>), g.blocks, threads, smem, st, data, g.k, g.c, g.s,
+                    g.ls, g.chunk_log, g.ctw, W, t->kw, tlo, thi, t->lb, g.tw_shift, xp);
+    ctx->prof_end(PROF_NTT_PASS, pslot, st);
+    return ZKR_OK;
+}
+
 // In-place transform of 2^log_n elements on `st`.
 //   dit == false: natural in  -> bit-reversed out (DIF)
 //   dit == true : bit-reversed in -> natural out  (DIT)
@@ -377,30 +425,121 @@ int ntt_run(zkr_ctx* ctx, cudaStream_t st, Fr* data, int log_n, bool dit, bool i
     }
     int ks[4];
     const int np = plan_passes(log_n, ks);
-    const Fr* W = inverse ? t->wsub_i : t->wsub_f;
-    const Fr* tlo = inverse ? t->tw_lo_i : t->tw_lo_f;
-    const Fr* thi = inverse ? t->tw_hi_i : t->tw_hi_f;
+    const NttXchg none = {};
     for (int step = 0; step < np; step++) {
         const int i = dit ? np - 1 - step : step;
-        int chunk_log = log_n;
-        for (int j = 0; j < i; j++) chunk_log -= ks[j];
-        const int k = ks[i];
-        const int s = chunk_log - k;
-        int c = kTileLog - k;
-        if (c > s) c = s;
-        const int T = k + c;
-        const int tile = 1 << T;
-        const int threads = tile / 8;
-        const size_t smem = (size_t)8 * (tile + (tile >> 3) + 4) * sizeof(uint32_t);
-        const unsigned blocks = 1u << (log_n - T);
-        // sub-NTT root: omega_{2^k} = W-table stride 2^(kw-k); the table is indexed in units of omega_{2^kw}
-        const int pslot = ctx->prof_begin(PROF_NTT_PASS, st, (double)((size_t)1 << log_n));
-        if (dit) ZKR_LAUNCH(ctx, k_ntt_pass<true>, blocks, threads, smem, st, data, k, c, s, chunk_log, W, t->kw,
-                            tlo, thi, t->lb, log_n - chunk_log);
-        else ZKR_LAUNCH(ctx, k_ntt_pass<false>, blocks, threads, smem, st, data, k, c, s, chunk_log, W, t->kw,
-                        tlo, thi, t->lb, log_n - chunk_log);
-        ctx->prof_end(PROF_NTT_PASS, pslot, st);
+        PassGeom g;
+        g.chunk_log = log_n;
+        for (int j = 0; j < i; j++) g.chunk_log -= ks[j];
+        g.k = ks[i];
+        g.s = g.chunk_log - g.k;
+        g.c = kTileLog - g.k;
+        if (g.c > g.s) g.c = g.s;
+        g.ls = g.s;
+        g.ctw = 0;
+        g.tw_shift = log_n - g.chunk_log;
+        g.blocks = 1u << (log_n - g.k - g.c);
+        ZKR_TRY(launch_pass<0>(ctx, st, t, data, g, dit, inverse, none, (double)((size_t)1 << log_n)));
     }
+    return ZKR_OK;
+}
+
+// Rows of the sharded four-step, 2^k0.  The passes after the exchange work on contiguous rows of 2^s0
+// elements and want full 2^11 tiles, so s0 is 11 (one local pass) up to 2^22 and >= 14 (a short pass + a
+// full one) above; k0 <= 9 there keeps >= 4 adjacent columns (128 contiguous bytes) per remote store
+// segment.  k0 >= g so that every rank owns whole rows.  ZKR_NTT_SHARD_K0 overrides (experiments).
+int ntt_sharded_k0(int log_n, int g) {
+    if (const char* e = getenv("ZKR_NTT_SHARD_K0")) {
+        const int v = atoi(e);
+        if (v >= g && v >= 3 && v <= kTileLog && v < log_n) return v;
+    }
+    int k0;
+    if (log_n >= 23) k0 = 9;
+    else if (log_n >= 14) k0 = log_n - kTileLog;
+    else k0 = log_n / 2;
+    if (k0 < g) k0 = g;
+    if (k0 < 3) k0 = 3;
+    return k0;
+}
+
+// passes over one row of 2^s0 elements: the last one is a full tile, the first takes the remainder
+static int plan_row_passes(int s0, int* ks) {
+    if (s0 <= kTileLog) {
+        ks[0] = s0;
+        return 1;
+    }
+    int np = 0, rem = s0;
+    int tmp[4];
+    while (rem > kTileLog) {
+        tmp[np++] = kTileLog;
+        rem -= kTileLog;
+    }
+    tmp[np++] = rem;
+    for (int i = 0; i < np; i++) ks[i] = tmp[np - 1 - i];
+    return np;
+}
+
+int ntt_run_sharded(zkr_ctx* ctx, cudaStream_t st, Fr* src, const NttXchg& x, int log_n, bool dit, bool inverse,
+                    int (*barrier)(void*, cudaStream_t), void* barrier_arg) {
+    NttTables* t;
+    ZKR_TRY(ntt_get_tables(ctx, log_n, &t));
+    const int g = x.g, k0 = x.k0, s0 = x.s0;
+    if (k0 != ntt_sharded_k0(log_n, g) || s0 != log_n - k0 || k0 < 3 || k0 > kTileLog || s0 - g < kTileLog - k0 ||
+        s0 < 3 || s0 > 3 * kTileLog) {
+        set_error("sharded NTT: 2^%d over 2^%d ranks is too small (or the geometry is inconsistent)", log_n, g);
+        return ZKR_E_UNSUPPORTED;
+    }
+    int ks[4];
+    const int np1 = plan_row_passes(s0, ks);      // passes over the columns of one row (local, contiguous rows)
+    const double units = (double)((size_t)1 << (log_n - g));
+    Fr* dst = x.peer[x.rank];
+    PassGeom g0;                                  // the strided pass over the rows, on a COLS slab
+    g0.k = k0;
+    g0.c = kTileLog - k0;
+    g0.s = s0;
+    g0.ls = s0 - g;
+    g0.chunk_log = 0;
+    g0.ctw = (unsigned)x.rank << (s0 - g);
+    g0.tw_shift = 0;
+    g0.blocks = 1u << (s0 - g - g0.c);
+    auto local_geom = [&](int i) {                // pass i (0-based) over the 2^(k0-g) local rows of 2^s0 columns
+        PassGeom q;
+        q.chunk_log = s0;
+        for (int j = 0; j < i; j++) q.chunk_log -= ks[j];
+        q.k = ks[i];
+        q.s = q.chunk_log - q.k;
+        q.c = kTileLog - q.k;
+        if (q.c > q.s) q.c = q.s;
+        q.ls = q.s;
+        q.ctw = 0;
+        q.tw_shift = log_n - q.chunk_log;
+        q.blocks = 1u << (log_n - g - q.k - q.c);
+        return q;
+    };
+    if (!dit) {
+        ZKR_TRY(barrier(barrier_arg, st));        // every rank is done with its destination buffer
+        ZKR_TRY(launch_pass<1>(ctx, st, t, src, g0, false, inverse, x, units));
+        ZKR_TRY(barrier(barrier_arg, st));        // all remote stores have landed
+        for (int i = 0; i < np1; i++) ZKR_TRY(launch_pass<0>(ctx, st, t, dst, local_geom(i), false, inverse, x, units));
+    } else {
+        for (int i = np1 - 1; i >= 1; i--) ZKR_TRY(launch_pass<0>(ctx, st, t, src, local_geom(i), true, inverse, x, units));
+        ZKR_TRY(barrier(barrier_arg, st));
+        ZKR_TRY(launch_pass<2>(ctx, st, t, src, local_geom(0), true, inverse, x, units));
+        ZKR_TRY(barrier(barrier_arg, st));
+        ZKR_TRY(launch_pass<3>(ctx, st, t, dst, g0, true, inverse, x, units));
+    }
+    return ZKR_OK;
+}
+
+int ntt_scale_pow_sharded(zkr_ctx* ctx, cudaStream_t st, Fr* x, const NttXchg& g, int log_n, int layout,
+                          const Fr* lo, const Fr* hi, int lb) {
+    const size_t nl = (size_t)1 << (log_n - g.g);
+    ZKR_LAUNCH(ctx, k_scale_pow_sharded, ceil_div(nl, 128), 128, 0, st, x, nl, log_n, lo, hi, lb, layout, g.s0, g.g, g.rank);
+    return ZKR_OK;
+}
+
+int ntt_scale_const(zkr_ctx* ctx, cudaStream_t st, Fr* x, size_t n, const Fr* cst) {
+    ZKR_LAUNCH(ctx, k_scale_const, ceil_div(n, 128), 128, 0, st, x, n, cst);
     return ZKR_OK;
 }
 

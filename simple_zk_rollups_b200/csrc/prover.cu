@@ -15,6 +15,7 @@
 #include <cstring>
 #include <thread>
 
+#include "comm_iface.cuh"
 #include "ec.cuh"
 #include "msm_iface.cuh"
 #include "ntt_iface.cuh"
@@ -25,6 +26,8 @@ struct zkr_pkey {
     zkr_ctx* ctx = nullptr;
     uint32_t n_vars = 0, n_public = 0, domain_size = 0;
     int log_m = 0;
+    int rank = 0, world = 1;       // world > 1: the five base sets hold this rank's point range only
+    uint64_t h_lo = 0;             // first h coefficient (bit-reversed order) of this rank's hExps slice
     // polsA / polsB as CSR by constraint row (coefficients Fr-M exactly as in the key)
     uint32_t *a_ptr = nullptr, *a_sig = nullptr, *b_ptr = nullptr, *b_sig = nullptr;
     Fr *a_coef = nullptr, *b_coef = nullptr;
@@ -111,6 +114,23 @@ __global__ void k_finish(const char* res, char* proof) {
     }
 }
 
+// sharded prove: res[e] = sum over ranks of the gathered partial results (block e: A, B1, C, H in G1; B2 in G2)
+__global__ void k_sum_res(const char* slots, int world, char* res) {
+    const int offs[5] = {R_A, R_B1, R_C, R_H, R_B2};
+    const int off = offs[blockIdx.x];
+    if (blockIdx.x < 4) {
+        G1XYZZ acc = G1XYZZ::load(slots + off);
+#pragma unroll 1
+        for (int r = 1; r < world; r++) acc.add(G1XYZZ::load(slots + (size_t)r * kCommSlotBytes + off));
+        acc.store(res + off);
+    } else {
+        G2XYZZ acc = G2XYZZ::load(slots + off);
+#pragma unroll 1
+        for (int r = 1; r < world; r++) acc.add(G2XYZZ::load(slots + (size_t)r * kCommSlotBytes + off));
+        acc.store(res + off);
+    }
+}
+
 struct PkView {
     uint32_t n, l, m, pA, pB, pPA, pPB1, pPB2, pPC, pPH;
 };
@@ -184,8 +204,15 @@ void pkey_release(zkr_pkey* pk) {
 
 }  // namespace
 
-extern "C" int zkr_pkey_load_bin(zkr_ctx* ctx, const void* vbuf, size_t len, zkr_pkey** out) {
-    if (!ctx || !vbuf || !out) return ZKR_E_INVALID;
+// [lo, hi) of `total` entries owned by `rank` (balanced to within one entry; mirrors sharding.point_range)
+static void shard_range(uint64_t total, int rank, int world, uint64_t* lo, uint64_t* hi) {
+    const uint64_t base = total / world, rem = total % world;
+    *lo = rank * base + ((uint64_t)rank < rem ? rank : rem);
+    *hi = *lo + base + ((uint64_t)rank < rem ? 1 : 0);
+}
+
+static int pkey_load(zkr_ctx* ctx, const void* vbuf, size_t len, int rank, int world, zkr_pkey** out) {
+    if (!ctx || !vbuf || !out || world < 1 || rank < 0 || rank >= world) return ZKR_E_INVALID;
     *out = nullptr;
     const uint8_t* buf = (const uint8_t*)vbuf;
     if (len < 488) {
@@ -211,7 +238,10 @@ extern "C" int zkr_pkey_load_bin(zkr_ctx* ctx, const void* vbuf, size_t len, zkr
     pk->n_vars = v.n;
     pk->n_public = v.l;
     pk->domain_size = v.m;
+    pk->rank = rank;
+    pk->world = world;
     while ((1u << pk->log_m) < v.m) pk->log_m++;
+    uint64_t lo = 0, hi = 0;
     int rc = ZKR_OK;
 #define PK_TRY(expr)              \
     do {                          \
@@ -256,14 +286,15 @@ extern "C" int zkr_pkey_load_bin(zkr_ctx* ctx, const void* vbuf, size_t len, zkr
         for (uint32_t i = 0; i < N + 2; i++) sidx[i] = i;            // n -> 1, n+1 -> r
         pk->A = bases_alloc();
         bases_set_group(pk->A, 1);
-        PK_TRY(bases_build_g1(ctx, pk->A, pts.data(), n + 2, 0, st, sidx.data()));
+        shard_range(n + 2, rank, world, &lo, &hi);
+        PK_TRY(bases_build_g1(ctx, pk->A, pts.data() + 64 * lo, hi - lo, 0, st, sidx.data() + lo));
         // B1' = [B1.., beta1, delta1] x [w.., 1, s]
         memcpy(pts.data(), buf + v.pPB1, 64 * n);
         memcpy(&pts[64 * n], beta1, 64);
         sidx[N + 1] = N + 2;                                          // s
         pk->B1 = bases_alloc();
         bases_set_group(pk->B1, 1);
-        PK_TRY(bases_build_g1(ctx, pk->B1, pts.data(), n + 2, 0, st, sidx.data()));
+        PK_TRY(bases_build_g1(ctx, pk->B1, pts.data() + 64 * lo, hi - lo, 0, st, sidx.data() + lo));
         // B2' = [B2.., beta2, delta2] x [w.., 1, s]
         std::vector<char> pts2(128ull * (n + 2));
         memcpy(pts2.data(), buf + v.pPB2, 128 * n);
@@ -271,7 +302,7 @@ extern "C" int zkr_pkey_load_bin(zkr_ctx* ctx, const void* vbuf, size_t len, zkr
         memcpy(&pts2[128 * (n + 1)], delta2, 128);
         pk->B2 = bases_alloc();
         bases_set_group(pk->B2, 2);
-        PK_TRY(bases_build_g2(ctx, pk->B2, pts2.data(), n + 2, 0, st, sidx.data()));
+        PK_TRY(bases_build_g2(ctx, pk->B2, pts2.data() + 128 * lo, hi - lo, 0, st, sidx.data() + lo));
     }
     {   // C' = [C_{l+1}.., delta1] x [w_{l+1}.., -rs]
         const uint64_t nc = n - l - 1;
@@ -283,7 +314,8 @@ extern "C" int zkr_pkey_load_bin(zkr_ctx* ctx, const void* vbuf, size_t len, zkr
         sidx[nc] = N + 3;
         pk->C = bases_alloc();
         bases_set_group(pk->C, 1);
-        PK_TRY(bases_build_g1(ctx, pk->C, pts.data(), nc + 1, 0, st, sidx.data()));
+        shard_range(nc + 1, rank, world, &lo, &hi);
+        PK_TRY(bases_build_g1(ctx, pk->C, pts.data() + 64 * lo, hi - lo, 0, st, sidx.data() + lo));
     }
     {   // H: hExps permuted to bit-reversed order (the H pipeline leaves h bit-reversed)
         std::vector<char> pts(64ull * m);
@@ -295,7 +327,9 @@ extern "C" int zkr_pkey_load_bin(zkr_ctx* ctx, const void* vbuf, size_t len, zkr
         }
         pk->H = bases_alloc();
         bases_set_group(pk->H, 1);
-        PK_TRY(bases_build_g1(ctx, pk->H, pts.data(), m, 0, st, nullptr));
+        shard_range(m, rank, world, &lo, &hi);
+        pk->h_lo = lo;
+        PK_TRY(bases_build_g1(ctx, pk->H, pts.data() + 64 * lo, hi - lo, 0, st, nullptr));
     }
     // work buffers
     auto dmalloc = [&](void** p, size_t bytes) -> int {
@@ -332,6 +366,14 @@ extern "C" int zkr_pkey_load_bin(zkr_ctx* ctx, const void* vbuf, size_t len, zkr
     return ZKR_OK;
 }
 
+extern "C" int zkr_pkey_load_bin(zkr_ctx* ctx, const void* vbuf, size_t len, zkr_pkey** out) {
+    return pkey_load(ctx, vbuf, len, 0, 1, out);
+}
+
+extern "C" int zkr_pkey_load_bin_sharded(zkr_ctx* ctx, const void* vbuf, size_t len, int rank, int world, zkr_pkey** out) {
+    return pkey_load(ctx, vbuf, len, rank, world, out);
+}
+
 extern "C" void zkr_pkey_free(zkr_pkey* pk) {
     if (!pk) return;
     DeviceGuard g(pk->ctx->device);
@@ -350,7 +392,7 @@ extern "C" int zkr_pkey_info(const zkr_pkey* pk, uint32_t* n_vars, uint32_t* n_p
 }
 
 // Queue one proof: witness already in pk->wext[0..n), (r|s) in pk->rs_dev.  Result -> d_proof.
-static int prove_enqueue(zkr_ctx* ctx, const zkr_pkey* pk, char* d_proof, bool timed) {
+static int prove_enqueue(zkr_ctx* ctx, const zkr_pkey* pk, char* d_proof, bool timed, zkr_comm* comm = nullptr) {
     const uint32_t n = pk->n_vars, m = pk->domain_size;
     cudaStream_t us = ctx->user_stream;
     cudaEvent_t const* ev = pk->ev;
@@ -372,7 +414,7 @@ static int prove_enqueue(zkr_ctx* ctx, const zkr_pkey* pk, char* d_proof, bool t
     if (timed) cudaEventRecord(ev[1], sH);
     ZKR_TRY(h_pipeline(ctx, sH, pk->at, pk->bt, pk->st, pk->h, pk->log_m, true));
     if (timed) cudaEventRecord(ev[2], sH);
-    ZKR_TRY(msm_run_g1(ctx, sH, pk->H, (const uint32_t*)pk->h, pk->res + R_H));
+    ZKR_TRY(msm_run_g1(ctx, sH, pk->H, (const uint32_t*)(pk->h + pk->h_lo), pk->res + R_H));
     if (timed) cudaEventRecord(ev[3], sH);
     // A, then s * pi_a
     if (timed) cudaEventRecord(ev[4], sA);
@@ -384,13 +426,23 @@ static int prove_enqueue(zkr_ctx* ctx, const zkr_pkey* pk, char* d_proof, bool t
     if (timed) cudaEventRecord(ev[10], sC);
     ZKR_TRY(msm_run_g1(ctx, sC, pk->C, w, pk->res + R_C));
     if (timed) cudaEventRecord(ev[11], sC);
-    // the two blinding scalar multiplications need A and B1
-    if (par) {
-        ZKR_CUDA(cudaEventRecord(ctx->ev_join[2], sB1));
-        ZKR_CUDA(cudaStreamWaitEvent(sA, ctx->ev_join[2], 0));
+    if (comm && comm->world > 1) {
+        // sharded: the five results are partial sums over this rank's point ranges.  Store them into every
+        // peer's gather slot, add the `world` partials, then blind (s*pi_a, r*pib1 need the full A, B1).
+        if (par) ZKR_TRY(ctx->join(5));
+        int parity = 0;
+        ZKR_TRY(comm_allgather_small(comm, us, pk->res, R_TOTAL, &parity));
+        ZKR_LAUNCH(ctx, k_sum_res, 5, 1, 0, us, comm_gather_slot(comm, comm->rank, parity, 0), comm->world, pk->res);
+        ZKR_LAUNCH(ctx, k_blind_muls, 2, 1, 0, us, pk->res, pk->wext, n);
+    } else {
+        // the two blinding scalar multiplications need A and B1
+        if (par) {
+            ZKR_CUDA(cudaEventRecord(ctx->ev_join[2], sB1));
+            ZKR_CUDA(cudaStreamWaitEvent(sA, ctx->ev_join[2], 0));
+        }
+        ZKR_LAUNCH(ctx, k_blind_muls, 2, 1, 0, sA, pk->res, pk->wext, n);
+        if (par) ZKR_TRY(ctx->join(5));
     }
-    ZKR_LAUNCH(ctx, k_blind_muls, 2, 1, 0, sA, pk->res, pk->wext, n);
-    if (par) ZKR_TRY(ctx->join(5));
     if (timed) cudaEventRecord(ev[12], us);
     ZKR_LAUNCH(ctx, k_finish, 3, 1, 0, us, (const char*)pk->res, d_proof);
     if (timed) cudaEventRecord(ev[13], us);
@@ -416,9 +468,13 @@ static int check_range_flags(zkr_ctx* ctx, const zkr_pkey* pk) {
     return ZKR_OK;
 }
 
-extern "C" int zkr_prove(zkr_ctx* ctx, const zkr_pkey* pk, const void* witness, size_t n_signals, const void* r32,
-                         const void* s32, void* out_proof, zkr_stats* stats) {
+static int prove_host(zkr_ctx* ctx, const zkr_pkey* pk, const void* witness, size_t n_signals, const void* r32,
+                      const void* s32, void* out_proof, zkr_stats* stats, zkr_comm* comm) {
     if (!ctx || !pk || !witness || !out_proof || pk->ctx != ctx) return ZKR_E_INVALID;
+    if (pk->world != (comm ? comm->world : 1) || (comm && (comm->rank != pk->rank || !comm->connected))) {
+        set_error("key was loaded for rank %d of %d; use the matching zkr_prove / zkr_prove_sharded call", pk->rank, pk->world);
+        return ZKR_E_INVALID;
+    }
     if (n_signals != pk->n_vars) {
         set_error("witness has %zu signals, key expects %u", n_signals, pk->n_vars);
         return ZKR_E_INVALID;
@@ -434,10 +490,11 @@ extern "C" int zkr_prove(zkr_ctx* ctx, const zkr_pkey* pk, const void* witness, 
     cudaEventRecord(ev[14], us);
     ZKR_CUDA(cudaMemcpyAsync(pk->wext, witness, 32ull * pk->n_vars, cudaMemcpyHostToDevice, us));
     ZKR_CUDA(cudaMemcpyAsync(pk->rs_dev, pin + 256, 64, cudaMemcpyHostToDevice, us));
-    ZKR_TRY(prove_enqueue(ctx, pk, pk->proof, true));
+    ZKR_TRY(prove_enqueue(ctx, pk, pk->proof, true, comm));
     ZKR_CUDA(cudaMemcpyAsync(pin, pk->proof, ZKR_PROOF_BYTES, cudaMemcpyDeviceToHost, us));
     cudaEventRecord(ev[15], us);
     ZKR_CUDA(cudaStreamSynchronize(us));
+    if (comm) ZKR_TRY(comm_check(comm, us));
     int rc = check_range_flags(ctx, pk);
     if (rc != ZKR_OK) return rc;
     memcpy(out_proof, pin, ZKR_PROOF_BYTES);
@@ -463,9 +520,21 @@ extern "C" int zkr_prove(zkr_ctx* ctx, const zkr_pkey* pk, const void* witness, 
     return ZKR_OK;
 }
 
+extern "C" int zkr_prove(zkr_ctx* ctx, const zkr_pkey* pk, const void* witness, size_t n_signals, const void* r32,
+                         const void* s32, void* out_proof, zkr_stats* stats) {
+    return prove_host(ctx, pk, witness, n_signals, r32, s32, out_proof, stats, nullptr);
+}
+
+extern "C" int zkr_prove_sharded(zkr_comm* comm, const zkr_pkey* pk, const void* witness, size_t n_signals,
+                                 const void* r32, const void* s32, void* out_proof, zkr_stats* stats) {
+    if (!comm) return ZKR_E_INVALID;
+    return prove_host(comm->ctx, pk, witness, n_signals, r32, s32, out_proof, stats, comm);
+}
+
 extern "C" int zkr_prove_dev(zkr_ctx* ctx, const zkr_pkey* pk, const void* d_witness, size_t n_signals,
                              const void* r32, const void* s32, void* d_out_proof) {
-    if (!ctx || !pk || !d_witness || !d_out_proof || pk->ctx != ctx || n_signals != pk->n_vars) return ZKR_E_INVALID;
+    if (!ctx || !pk || !d_witness || !d_out_proof || pk->ctx != ctx || n_signals != pk->n_vars || pk->world != 1)
+        return ZKR_E_INVALID;
     DeviceGuard g(ctx->device);
     cudaStream_t us = ctx->user_stream;
     char* pin = (char*)pk->pinned;

@@ -46,6 +46,26 @@ class Groth16Prover:
         self._keys.append(h)
         return h
 
+    def load_key_sharded(self, pk_bin, rank, world):
+        """Keep only `rank`'s point range of the five base sets (one proof split over `world` GPUs)."""
+        arr = np.frombuffer(pk_bin, dtype=np.uint8) if isinstance(pk_bin, (bytes, bytearray)) else pk_bin
+        h = C.c_void_p()
+        _lib.check(self.L.zkr_pkey_load_bin_sharded(self.ctx, _lib.buf_ptr(arr), arr.size, rank, world, C.byref(h)))
+        self._keys.append(h)
+        return h
+
+    def prove_sharded(self, comm, key, witness_bin, r=0, s=0):
+        """comm: sharding.Comm of this rank (all ranks call with the same witness, r, s) -> (proof, stats);
+        every rank returns the same 256 bytes as prove() on one GPU."""
+        w = np.frombuffer(witness_bin, dtype=np.uint8) if isinstance(witness_bin, (bytes, bytearray)) else witness_bin
+        out = np.zeros(_lib.PROOF_BYTES, dtype=np.uint8)
+        st = _lib.Stats()
+        rb = np.frombuffer(int(r).to_bytes(32, "little"), dtype=np.uint8)
+        sb = np.frombuffer(int(s).to_bytes(32, "little"), dtype=np.uint8)
+        _lib.check(self.L.zkr_prove_sharded(comm.h, key, _lib.buf_ptr(w), w.size // 32, _lib.buf_ptr(rb),
+                                            _lib.buf_ptr(sb), _lib.buf_ptr(out), C.byref(st)))
+        return out.tobytes(), st.as_dict()
+
     def key_info(self, key):
         a, b, c, d = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint64()
         _lib.check(self.L.zkr_pkey_info(key, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))

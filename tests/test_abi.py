@@ -73,3 +73,14 @@ def test_bench_contract_flags():
     assert out.returncode == 0
     for flag in ("--gpus", "--steps", "--warmup", "--impl"):
         assert flag in out.stdout
+
+
+def test_sharded_rows_log_python_mirror_matches_library():
+    """pure host logic of the sharded NTT plan (no GPU needed): the Python mirror equals the library."""
+    import os
+    from simple_zk_rollups_b200 import _lib, sharding as sh
+    assert "ZKR_NTT_SHARD_K0" not in os.environ
+    L = _lib.lib()
+    for world in (1, 2, 4, 8):
+        for log_n in range(8, 28):
+            assert L.zkr_ntt_sharded_rows_log(log_n, world) == sh.rows_log_default(log_n, world), (log_n, world)
