@@ -129,6 +129,7 @@ extern "C" int zkr_comm_create(zkr_ctx* ctx, int rank, int world, size_t max_ele
     cudaMemset(c->slab, 0, kCommHeaderBytes);
     cudaMalloc(&c->d_err, sizeof(int));
     cudaMemset(c->d_err, 0, sizeof(int));
+    cudaMalloc(&c->d_small, 512);
     c->peer_slab[rank] = c->slab;
     c->connected = world == 1;
     ZKR_CUDA(cudaDeviceSynchronize());
@@ -225,6 +226,7 @@ extern "C" void zkr_comm_destroy(zkr_comm* c) {
         if (c->ipc_open[r]) cudaIpcCloseMemHandle(c->peer_slab[r]);
     cudaFree(c->slab);
     cudaFree(c->d_err);
+    cudaFree(c->d_small);
     delete c;
 }
 
@@ -248,10 +250,8 @@ extern "C" int zkr_msm_sharded(zkr_comm* c, const zkr_bases* b, const void* scal
     }
     const int group = bases_group(b);
     const size_t xb = group == 1 ? 128 : 256, ob = group == 1 ? 64 : 128;
-    void* d_part;
-    ZKR_TRY(ctx->scratch_get("msm_partial", 256, &d_part));
-    void* d_aff;
-    ZKR_TRY(ctx->scratch_get("msm_out", 256, &d_aff));
+    void* d_part = c->d_small;
+    void* d_aff = c->d_small + 256;
     if (group == 1) ZKR_TRY(msm_run_g1(ctx, st, b, d_sc, d_part));
     else ZKR_TRY(msm_run_g2(ctx, st, b, d_sc, d_part));
     int parity = 0;

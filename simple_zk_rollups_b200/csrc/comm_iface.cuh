@@ -21,6 +21,7 @@ struct zkr_comm {
     uint32_t epoch = 0;                   // barriers issued so far
     uint32_t gather_seq = 0;              // gathers issued so far (slot parity)
     int* d_err = nullptr;                 // device flag: a barrier timed out
+    char* d_small = nullptr;              // 512 B: partial (256) | affine result (256) of a sharded MSM
     bool connected = false;
 };
 

@@ -336,71 +336,83 @@ __device__ __forceinline__ void mul_small_mem(XYZZ<F>* p, XYZZ<F>* tmp, uint32_t
     }
 }
 
-constexpr int kReduceThreads = 256;
+// One warp per CTA: these kernels are latency chains (tree levels of ~4 us point additions) that run
+// beside the other MSMs' bulk kernels; a 256-thread CTA of idle tree threads pins 33-65 K registers of an SM
+// (measured: the overlapped proof got 0.8 ms SLOWER with 256-thread reduction CTAs although the serialised
+// one got 2.4 ms faster).  32 threads x up to 255 registers leave the SM to the accumulation kernels.
+constexpr int kReduceThreads = 32;
 
-// stage 1: thread u owns buckets [uK, (u+1)K): running sums, then per block
-//   X_g = sum_l acc_l,  Y_g = sum_l l * S_l,  Z_g = sum_l S_l        (3 points per block)
+// Bucket reduction  sum_b (b+1) B_b  without a serial running sum.  Split b = hi * 2^lc + lo:
+//     sum_b b B_b = 2^lc * sum_hi hi * Row[hi]  +  sum_lo lo * Col[lo],      sum_b B_b = sum_hi Row[hi]
+// with Row[hi] = sum_lo B[hi, lo] and Col[lo] = sum_hi B[hi, lo] (plain sums: one CTA each, tree-reduced),
+// and each weighted sum over <= 2^12 entries by bit decomposition,  sum_i i S_i = sum_j 2^j (sum_{i: bit j} S_i):
+// one CTA per bit does a plain masked sum and its doublings; the last CTA to finish adds the <= 24 terms.
+// Every bucket is added exactly twice (like the running sum) but every addition is independent, so the
+// latency of the reduction is ~2 tree depths + (c-2) doublings instead of thousands of chained additions.
+
+// stage 1: CTA g < 2^lr: Row[g];  CTA 2^lr + l: Col[l]
 template <class F>
 __global__ void __launch_bounds__(kReduceThreads)
-k_reduce_stage1(const XYZZ<F>* __restrict__ buckets, uint32_t nbuckets, uint32_t K, XYZZ<F>* __restrict__ out) {
+k_bucket_sums(const XYZZ<F>* __restrict__ buckets, int lr, int lc, XYZZ<F>* __restrict__ out) {
     extern __shared__ unsigned char smraw[];
     XYZZ<F>* s0 = reinterpret_cast<XYZZ<F>*>(smraw);
-    XYZZ<F>* s1 = s0 + kReduceThreads;
-    const int l = threadIdx.x;
-    const uint32_t u = blockIdx.x * kReduceThreads + l;
-    XYZZ<F> run = XYZZ<F>::identity(), acc = XYZZ<F>::identity();
-    const uint64_t b0 = (uint64_t)u * K;
+    const uint32_t t = threadIdx.x, g = blockIdx.x;
+    const bool row = g < (1u << lr);
+    const uint32_t len = row ? (1u << lc) : (1u << lr);
+    const XYZZ<F>* base = row ? buckets + ((size_t)g << lc) : buckets + (g - (1u << lr));
+    const size_t stride = row ? 1 : ((size_t)1 << lc);
+    if (t < len) s0[t] = base[t * stride];
+    else s0[t] = XYZZ<F>::identity();
 #pragma unroll 1
-    for (int b = (int)K - 1; b >= 0; b--) {
-        if (b0 + b < nbuckets) {
-            run.add(XYZZ<F>::load(buckets + b0 + b));
-            acc.add(run);
-        }
-    }
-    s0[l] = acc;
+    for (uint32_t i = t + kReduceThreads; i < len; i += kReduceThreads) xyzz_add_mem(&s0[t], &s0[t], &base[i * stride]);
     block_sum_inplace<F, kReduceThreads>(s0);
-    if (l == 0) s0[0].store(out + 3 * blockIdx.x);            // X_g
-    __syncthreads();
-    s0[l] = run;
-    XYZZ<F>* T = block_suffix_scan<F, kReduceThreads>(s0, s1);
-    if (l == 0) {
-        T[0].store(out + 3 * blockIdx.x + 2);                 // Z_g = T_0
-        T[0] = XYZZ<F>::identity();
-    }
-    block_sum_inplace<F, kReduceThreads>(T);                  // sum_{l>=1} T_l = sum_l l*S_l
-    if (l == 0) T[0].store(out + 3 * blockIdx.x + 1);         // Y_g
+    if (t == 0) out[g] = s0[0];
 }
 
-// stage 2 (one block): total = sum X + K sum Y + 256 K sum_g g Z_g
+// stage 2: CTA j < lr: 2^(j+lc) * sum_{hi: bit j} Row[hi];  CTA lr + j, j < lc: 2^j * sum_{lo: bit j} Col[lo];
+//          CTA lr + lc: sum_hi Row[hi].  terms -> sums[2^lr + 2^lc ..]; the last CTA adds them into *out.
 template <class F>
 __global__ void __launch_bounds__(kReduceThreads)
-k_reduce_stage2(const XYZZ<F>* __restrict__ in, uint32_t G, uint32_t K, XYZZ<F>* __restrict__ out) {
+k_bucket_weighted(XYZZ<F>* __restrict__ sums, int lr, int lc, unsigned int* __restrict__ counter, XYZZ<F>* __restrict__ out) {
     extern __shared__ unsigned char smraw[];
     XYZZ<F>* s0 = reinterpret_cast<XYZZ<F>*>(smraw);
-    XYZZ<F>* s1 = s0 + kReduceThreads;
-    __shared__ XYZZ<F> res[3];
-    const uint32_t g = threadIdx.x;
-    const XYZZ<F> id = XYZZ<F>::identity();
-    s0[g] = g < G ? XYZZ<F>::load(in + 3 * g) : id;
+    __shared__ bool last;
+    const uint32_t t = threadIdx.x;
+    const int g = blockIdx.x, nterms = lr + lc + 1;
+    const bool row = g < lr || g == lr + lc;
+    const int bit = g == lr + lc ? -1 : (g < lr ? g : g - lr);
+    const uint32_t len = row ? (1u << lr) : (1u << lc);
+    const XYZZ<F>* src = row ? sums : sums + ((size_t)1 << lr);
+    XYZZ<F>* terms = sums + ((size_t)1 << lr) + ((size_t)1 << lc);
+    s0[t] = XYZZ<F>::identity();
+#pragma unroll 1
+    for (uint32_t i = t; i < len; i += kReduceThreads)
+        if (bit < 0 || ((i >> bit) & 1)) xyzz_add_mem(&s0[t], &s0[t], &src[i]);
     block_sum_inplace<F, kReduceThreads>(s0);
-    if (g == 0) res[0] = s0[0];                               // sum X
+    if (t == 0) {
+        const int dbl = bit < 0 ? 0 : (g < lr ? bit + lc : bit);
+#pragma unroll 1
+        for (int d = 0; d < dbl; d++) xyzz_dbl_mem(&s0[0]);
+        terms[g] = s0[0];
+        __threadfence();
+        last = atomicAdd(counter, 1u) == (unsigned)(nterms - 1);
+    }
     __syncthreads();
-    s0[g] = g < G ? XYZZ<F>::load(in + 3 * g + 1) : id;
+    if (!last) return;
+    __threadfence();
+    if (t < (uint32_t)nterms) {
+        // written by other CTAs of this launch: read through L2
+        const uint4* src16 = reinterpret_cast<const uint4*>(terms + t);
+        uint4* dst16 = reinterpret_cast<uint4*>(s0 + t);
+#pragma unroll
+        for (int i = 0; i < (int)(sizeof(XYZZ<F>) / 16); i++) dst16[i] = __ldcg(src16 + i);
+    } else {
+        s0[t] = XYZZ<F>::identity();
+    }
     block_sum_inplace<F, kReduceThreads>(s0);
-    if (g == 0) res[1] = s0[0];                               // sum Y
-    __syncthreads();
-    s0[g] = g < G ? XYZZ<F>::load(in + 3 * g + 2) : id;
-    XYZZ<F>* T = block_suffix_scan<F, kReduceThreads>(s0, s1);
-    if (g == 0) T[0] = id;
-    block_sum_inplace<F, kReduceThreads>(T);                  // sum_g g*Z_g
-    if (g == 0) {
-        XYZZ<F>* r = &T[0];
-        XYZZ<F>* tmp = &T[1];
-        mul_small_mem(r, tmp, kReduceThreads);
-        xyzz_add_mem(r, r, &res[1]);
-        mul_small_mem(r, tmp, K);
-        xyzz_add_mem(r, r, &res[0]);
-        r->store(out);
+    if (t == 0) {
+        s0[0].store(out);
+        *counter = 0;
     }
 }
 
@@ -420,7 +432,8 @@ struct MsmWork {                      // per-bases device work buffers
     void* buckets = nullptr;
     void* bnd[2] = {nullptr, nullptr};
     uint32_t* bnd_keys[2] = {nullptr, nullptr};
-    void* red = nullptr;              // 3 * G points
+    void* red = nullptr;              // 2^lr + 2^lc row / column sums, then lr + lc + 1 weighted terms
+    unsigned int* red_counter = nullptr;
     void* result = nullptr;           // 1 XYZZ
     int* range_err = nullptr;
     size_t bytes = 0;
@@ -526,17 +539,21 @@ int bases_build(zkr_ctx* ctx, zkr_bases* b, const char* h_points, size_t n_src, 
     ZKR_CUDA(cudaMalloc(&wk.bnd[1], XB * bnd1));
     ZKR_CUDA(cudaMalloc(&wk.bnd_keys[0], 4 * bnd0));
     ZKR_CUDA(cudaMalloc(&wk.bnd_keys[1], 4 * bnd1));
-    ZKR_CUDA(cudaMalloc(&wk.red, XB * 3 * kReduceThreads));
+    const int rlc = (b->plan.c - 1) / 2, rlr = b->plan.c - 1 - rlc;
+    const size_t nred = ((size_t)1 << rlr) + ((size_t)1 << rlc) + 32;
+    ZKR_CUDA(cudaMalloc(&wk.red, XB * nred));
+    ZKR_CUDA(cudaMalloc(&wk.red_counter, sizeof(unsigned int)));
+    ZKR_CUDA(cudaMemsetAsync(wk.red_counter, 0, sizeof(unsigned int), st));
     ZKR_CUDA(cudaMalloc(&wk.result, XB));
     ZKR_CUDA(cudaMalloc(&wk.range_err, sizeof(int)));
     ZKR_CUDA(cudaMemsetAsync(wk.range_err, 0, sizeof(int), st));
-    wk.bytes += wk.cub_bytes + XB * ((size_t)b->plan.nbuckets + bnd0 + bnd1 + 3 * kReduceThreads + 1) + 4 * (bnd0 + bnd1);
+    wk.bytes += wk.cub_bytes + XB * ((size_t)b->plan.nbuckets + bnd0 + bnd1 + nred + 1) + 4 * (bnd0 + bnd1);
     b->bytes += wk.bytes;
     static bool attr_done[2] = {false, false};
     const int which = sizeof(F) == 32 ? 0 : 1;
     if (!attr_done[which]) {
-        ZKR_CUDA(cudaFuncSetAttribute(k_reduce_stage1<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * XB * kReduceThreads)));
-        ZKR_CUDA(cudaFuncSetAttribute(k_reduce_stage2<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * XB * kReduceThreads)));
+        ZKR_CUDA(cudaFuncSetAttribute(k_bucket_sums<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(XB * kReduceThreads)));
+        ZKR_CUDA(cudaFuncSetAttribute(k_bucket_weighted<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(XB * kReduceThreads)));
         ZKR_CUDA(cudaFuncSetAttribute((k_accum_affine<F, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
         ZKR_CUDA(cudaFuncSetAttribute((k_accum_affine<F, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
         attr_done[which] = true;
@@ -593,16 +610,12 @@ int msm_run(zkr_ctx* ctx, cudaStream_t st, const zkr_bases* b, const uint32_t* d
         cnt = 2 * T;          // threads past T only pad their block; their slots are never read
         cur ^= 1;
     }
-    // bucket reduction
-    // 16 buckets per thread: the block-level scan costs ~2600 point additions per CTA, so CTAs are kept few
-    // (total work stays ~1.3x the running sums and hides behind the other MSMs' bulk kernels); measured:
-    // one bucket per thread (256 CTAs) is no faster in isolation and 2 ms slower per overlapped proof.
-    uint32_t G = nb / (kReduceThreads * 16);
-    if (G < 1) G = 1;
-    if (G > 128) G = 128;
-    const uint32_t K = (nb + G * kReduceThreads - 1) / (G * kReduceThreads);
-    ZKR_LAUNCH(ctx, k_reduce_stage1<F>, G, kReduceThreads, 2 * XB * kReduceThreads, st, buckets, nb, K, (XYZZ<F>*)wk.red);
-    ZKR_LAUNCH(ctx, k_reduce_stage2<F>, 1, kReduceThreads, 2 * XB * kReduceThreads, st, (const XYZZ<F>*)wk.red, G, K, d_out);
+    // bucket reduction: row / column sums, then bit-decomposed weighted sums (see k_bucket_sums)
+    const int lc = (c - 1) / 2, lr = c - 1 - lc;
+    ZKR_LAUNCH(ctx, k_bucket_sums<F>, (1u << lr) + (1u << lc), kReduceThreads, XB * kReduceThreads, st, buckets, lr, lc,
+               (XYZZ<F>*)wk.red);
+    ZKR_LAUNCH(ctx, k_bucket_weighted<F>, lr + lc + 1, kReduceThreads, XB * kReduceThreads, st, (XYZZ<F>*)wk.red, lr, lc,
+               wk.red_counter, d_out);
     return ZKR_OK;
 }
 

@@ -3,6 +3,13 @@ import sys
 
 import pytest
 
+# The multi-rank tests emulate several GPUs' ranks on ONE device (tests/test_gpu_sharded.py): a rank's barrier
+# kernel spins until its peers arrive, so nothing a peer's host thread does may wait for the whole device.
+# Lazy module loading does exactly that on a kernel's first launch, and streams that share a hardware queue
+# serialise behind the spinning kernel -- both are artefacts of sharing a device, not of the multi-GPU path.
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for _p in (ROOT, os.path.join(ROOT, "tests")):
     if _p not in sys.path:
