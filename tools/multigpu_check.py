@@ -31,6 +31,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ntt-logs", default="20,22,24")
     ap.add_argument("--msm-logs", default="20,22")
+    ap.add_argument("--prove-shapes", default="", help="comma list of synth.SHAPES to prove sharded over all ranks (e.g. tx_2p20)")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--out", default=None)
     args = ap.parse_args()
@@ -51,7 +52,7 @@ def main():
     comm = sh.Comm(ctx, rank, world, (1 << max(ntt_logs + [16])) // world)
     if world > 1:
         comm.connect_torch()
-    res = {"world": world, "ntt": [], "msm": []}
+    res = {"world": world, "ntt": [], "msm": [], "prove": []}
 
     def barrier():
         torch.cuda.synchronize()
@@ -164,6 +165,46 @@ def main():
             print(json.dumps(row), flush=True)
         L.zkr_bases_free(bases)
         del d_k
+    # ------------------------------------------------------------------ one proof split over all ranks
+    for shape in [v for v in args.prove_shapes.split(",") if v]:
+        from simple_zk_rollups_b200 import keygen, synth
+        toxic = (0x1234567890ABCDEF1234567890ABCDEF1234567, 0x2222222222222222222222222222222222221,
+                 0x3333333333333333333333333333333333333331, 0x44444444444444444444444444444444441,
+                 0x555555555555555555555555555555555555555551)
+        nc, npub = synth.SHAPES[shape]
+        r1, w = synth.generate(nc, npub, seed=11)
+        pk_bin, _ = keygen.synth_setup(ctx, r1, toxic)
+        wit = np.frombuffer(synth.witness_bytes(w), dtype=np.uint8)
+        rb = np.frombuffer(int(0x1F2E3D4C5B6A7988 << 64 | 5).to_bytes(32, "little"), dtype=np.uint8)
+        sb = np.frombuffer(int(0x0123456789ABCDEF << 100 | 77).to_bytes(32, "little"), dtype=np.uint8)
+        full, part = C.c_void_p(), C.c_void_p()
+        _lib.check(L.zkr_pkey_load_bin(ctx, _lib.buf_ptr(pk_bin), pk_bin.size, C.byref(full)))
+        want = np.zeros(256, dtype=np.uint8)
+        st1 = _lib.Stats()
+
+        def prove_single():
+            _lib.check(L.zkr_prove(ctx, full, _lib.buf_ptr(wit), wit.size // 32, _lib.buf_ptr(rb), _lib.buf_ptr(sb),
+                                   _lib.buf_ptr(want), C.byref(st1)))
+        t_single = timed(prove_single, args.reps)
+        L.zkr_pkey_free(full)
+        _lib.check(L.zkr_pkey_load_bin_sharded(ctx, _lib.buf_ptr(pk_bin), pk_bin.size, rank, world, C.byref(part)))
+        got = np.zeros(256, dtype=np.uint8)
+        st2 = _lib.Stats()
+
+        def prove_sharded():
+            _lib.check(L.zkr_prove_sharded(comm.h, part, _lib.buf_ptr(wit), wit.size // 32, _lib.buf_ptr(rb),
+                                           _lib.buf_ptr(sb), _lib.buf_ptr(got), C.byref(st2)))
+        t_sh = timed(prove_sharded, args.reps)
+        same = torch.tensor([int(np.array_equal(got, want))], device="cuda")
+        if world > 1:
+            dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        L.zkr_pkey_free(part)
+        row = dict(shape=shape, world=world, constraints=nc, single_gpu_ms=round(t_single, 3), sharded_ms=round(t_sh, 3),
+                   speedup=round(t_single / t_sh, 3), identical_to_single_gpu_proof=bool(same.item()),
+                   sharded_stage_ms={k: round(v, 3) for k, v in st2.as_dict().items() if k.endswith("_ms")})
+        res["prove"].append(row)
+        if rank == 0:
+            print(json.dumps(row), flush=True)
     if rank == 0 and args.out:
         os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
         json.dump(res, open(args.out, "w"), indent=1)
@@ -173,6 +214,7 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     bad = [r for r in res["ntt"] if not r["correct"]] + [r for r in res["msm"] if r["correct"] is False or not r["ranks_agree"]]
+    bad += [r for r in res["prove"] if not r["identical_to_single_gpu_proof"]]
     sys.exit(1 if bad else 0)
 
 
