@@ -106,6 +106,23 @@ void zkr_pkey_free(zkr_pkey* pk);
 int zkr_pkey_info(const zkr_pkey* pk, uint32_t* n_vars, uint32_t* n_public, uint32_t* domain_size,
                   uint64_t* device_bytes);
 
+/* ---- key / witness ingestion from the snarkjs JSON text ------------ */
+/* binarifyProvingKey (operator/src/utils/binarify.ts:50-207) applied to the TEXT of a snarkjs
+ * `--protocol groth` proving key (proving_key.json, fields per SURVEY.md A.3): one streaming pass,
+ * output byte-identical to the reference's ArrayBuffer.  Values may be decimal strings
+ * (stringifyBigInts) or bare JSON integers; key order is free; polsC and unknown fields are
+ * skipped.  *out_buf is allocated by the library: release it with zkr_buf_free.  Host-only
+ * (no device needed).  Errors: ZKR_E_BADKEY (message names the byte offset), ZKR_E_UNSUPPORTED
+ * if the layout would exceed the format's 32-bit offsets, ZKR_E_NOMEM. */
+int zkr_pkey_json_to_bin(const char* json, size_t len, void** out_buf, size_t* out_len);
+/* binarifyWitness (binarify.ts:10-48) applied to the text of a witness.json (array of decimal
+ * strings / integers): n x 32 B little-endian, std form, values written as is. */
+int zkr_witness_json_to_bin(const char* json, size_t len, void** out_buf, size_t* out_len);
+void zkr_buf_free(void* buf);
+/* zkr_pkey_json_to_bin + zkr_pkey_load_bin: what replaces
+ * `binarifyProvingKey(provingKey)` at operator/src/snarks/common.ts:28, once per circuit. */
+int zkr_pkey_load_json(zkr_ctx* ctx, const char* json, size_t len, zkr_pkey** out);
+
 /* ---- prove -------------------------------------------------------------------------- */
 /* witness: n_signals x 32 B std form (binarifyWitness layout), HOST memory.
  * r32 / s32: blinding scalars, 32 B std form < r, or NULL for 0 (the snarkjs debug mode;

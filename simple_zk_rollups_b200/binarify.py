@@ -6,7 +6,12 @@ Same names, argument meaning and output bytes as the reference's TypeScript:
 In the reference both run on every proof (common.ts:27-28); here binarifyProvingKey runs once per
 circuit and its output is handed to Groth16Prover.load_key (zkr_pkey_load_bin).
 Inputs follow the snarkjs JSON schema (decimal strings or ints; stringifybigint semantics).
+
+binarifyProvingKeyJson / binarifyWitnessJson take the JSON TEXT (proving_key.json / witness.json as the
+reference `require`s them, operator/src/snarks/tx.ts:3) and run the native streaming converter of libzkr
+(csrc/keyjson.cu): same bytes, no per-coordinate big-integer objects.
 """
+import ctypes as _C
 import struct
 
 Q = 21888242871839275222246405745257275088696311157297823662689037894645226208583   # binarify.ts:80
@@ -79,3 +84,25 @@ def proof_from_bytes(buf):
     v = [str(int.from_bytes(buf[i * 32:(i + 1) * 32], "little")) for i in range(8)]
     return {"pi_a": [v[0], v[1], "1"], "pi_b": [[v[2], v[3]], [v[4], v[5]], ["1", "0"]],
             "pi_c": [v[6], v[7], "1"], "protocol": "groth"}
+
+
+def _native_json_to_bin(fn_name, text):
+    from . import _lib
+    L = _lib.lib()
+    data = text.encode() if isinstance(text, str) else bytes(text)
+    out, n = _C.c_void_p(), _C.c_size_t()
+    _lib.check(getattr(L, fn_name)(data, len(data), _C.byref(out), _C.byref(n)))
+    try:
+        return _C.string_at(out, n.value)
+    finally:
+        L.zkr_buf_free(out)
+
+
+def binarifyProvingKeyJson(text):
+    """binarifyProvingKey applied to the text of a snarkjs proving_key.json (zkr_pkey_json_to_bin)."""
+    return _native_json_to_bin("zkr_pkey_json_to_bin", text)
+
+
+def binarifyWitnessJson(text):
+    """binarifyWitness applied to the text of a witness.json (zkr_witness_json_to_bin)."""
+    return _native_json_to_bin("zkr_witness_json_to_bin", text)

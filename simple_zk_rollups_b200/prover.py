@@ -46,6 +46,14 @@ class Groth16Prover:
         self._keys.append(h)
         return h
 
+    def load_key_json(self, text):
+        """text: the snarkjs proving_key.json TEXT (str / bytes).  Native parse + binarify + upload, once."""
+        data = text.encode() if isinstance(text, str) else bytes(text)
+        h = C.c_void_p()
+        _lib.check(self.L.zkr_pkey_load_json(self.ctx, data, len(data), C.byref(h)))
+        self._keys.append(h)
+        return h
+
     def load_key_sharded(self, pk_bin, rank, world):
         """Keep only `rank`'s point range of the five base sets (one proof split over `world` GPUs)."""
         arr = np.frombuffer(pk_bin, dtype=np.uint8) if isinstance(pk_bin, (bytes, bytearray)) else pk_bin

@@ -134,6 +134,27 @@ def test_api_mirror(gp):
         gen_bad({})
 
 
+def test_prove_from_json_text(gp):
+    """proving_key.json / witness.json TEXT -> native ingestion -> resident key -> proof,
+    identical to the proof from the binarified key, in the reference's genTxVerifierProof shape."""
+    import json
+    r1, w = synth.generate(90, 4, seed=21)
+    pk, vk, _ = g.setup(r1.to_dicts(), TOXIC)
+    text = json.dumps(bf.pk_to_json(pk), indent=1)
+    key = gp.load_key_json(text)
+    info = gp.key_info(key)
+    assert (info["nVars"], info["nPublic"], info["domainSize"]) == (pk["nVars"], pk["nPublic"], pk["domainSize"])
+    wbin = binarify.binarifyWitnessJson(json.dumps([str(x) for x in w]))
+    assert wbin == bf.binarify_witness(w)
+    got, _ = gp.prove(key, wbin, 11, 13)
+    want, pub = g.gen_proof(pk, w, 11, 13)
+    assert got == g.proof_to_bytes(want)
+    assert g.verify(vk, g.proof_from_bytes(got), pub)
+    with pytest.raises(_lib.ZkrError) as ei:
+        gp.load_key_json(text[:-20])
+    assert ei.value.code == -2
+
+
 @pytest.mark.parametrize("shape", ["withdraw", "tx", "tx_2p20"])
 def test_prove_full_size(gp, shape):
     """BASELINE configs[0..1] at full size: GPU setup -> prove -> toxic-waste exponent check (no MSM / NTT
