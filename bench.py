@@ -29,6 +29,8 @@ sys.path.insert(0, ROOT)
 TOXIC = (0x1234567890ABCDEF1234567890ABCDEF1234567, 0x2222222222222222222222222222222222221,
          0x3333333333333333333333333333333333333331, 0x44444444444444444444444444444444441,
          0x555555555555555555555555555555555555555551)
+BASELINE_CONFIG = {"tx": "BASELINE.json configs[0]", "tx_2p20": "BASELINE.json configs[1]",
+                   "tx_2p22": "BASELINE.json configs[4] (per-GPU unit of the throughput batch)"}
 MODMUL_IMAD = 136            # 8x8-limb CIOS: 128 wide MACs + 8
 MADD_MODMULS = 10            # XYZZ mixed add 8M + 2S
 
@@ -243,7 +245,7 @@ def run_ours(args):
                             "note": "64 B per element per pass (read once + write once); the pass is IMAD-bound "
                                     "(~6 modmul per 64 B), see DESIGN.md"}
         # ---- CPU baseline: the C restatement of the reference algorithm on this box's host cores
-        cpu = cpu_baseline(pk_bin, wbytes, rs, out.tobytes(), args)
+        cpu = None if args.no_cpu else cpu_baseline(pk_bin, wbytes, rs, out.tobytes(), args)
         value = world * args.steps / (ms * 1e-3)
         e2e_val = world * args.steps / (ms_e2e * 1e-3)
         result = {
@@ -254,7 +256,8 @@ def run_ours(args):
             "config": {"workload": "BN254 Groth16 prove, rollup-shaped circuit %s: %d constraints, %d public, nVars %d, "
                                    "domain 2^%d; fixed (r,s); key resident in HBM" % (
                                        args.shape, r1.nConstraints, r1.nPublic, n, m.bit_length() - 1),
-                       "baseline_config": "BASELINE.json configs[1]", "parallelism": "one independent proof per GPU",
+                       "baseline_config": BASELINE_CONFIG.get(args.shape, "BASELINE.json configs[1] shape family"),
+                       "parallelism": "one independent proof per GPU",
                        "l2": "per-proof working set (%.1f GB of window tables + sort buffers) >> 126 MB L2; no flush needed" % (
                            info["device_bytes"] / 1e9)},
             "prove_ms": round(ms / args.steps, 4), "prove_ms_e2e": round(ms_e2e / args.steps, 4),
@@ -335,7 +338,7 @@ def run_reference(args):
         "data": "synthetic",
         "config": {"workload": "BN254 Groth16 prove, rollup-shaped circuit %s: %d constraints, %d public, nVars %d, "
                                "domain 2^%d; fixed (r,s)" % (args.shape, r1.nConstraints, r1.nPublic, n, bits),
-                   "baseline_config": "BASELINE.json configs[1]"},
+                   "baseline_config": BASELINE_CONFIG.get(args.shape, "BASELINE.json configs[1] shape family")},
         "cpu_baseline": {"value": round(val, 5), "unit": "proofs/s", "cores": cores, "kind": "port",
                          "sample": "every step is 1 full proof of the workload (C restatement of websnark groth16GenProof: "
                                    "Pippenger multiexp + iterative NTT on all host threads)"},
@@ -351,6 +354,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--shape", default="tx_2p20", help="withdraw | tx | tx_2p20 | tx_2p22 (simple_zk_rollups_b200.synth.SHAPES)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs under ncu)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         log("[bench] note: timing rules ask for >= 3 warm-up steps")

@@ -143,6 +143,35 @@ int zkr_prove_batch(zkr_ctx* const* ctxs, const zkr_pkey* const* pks, int n_ctx,
                     const void* const* witnesses, size_t n_signals, int n_proofs,
                     const void* rs32 /* n_proofs x 64 B (r|s) or NULL */, void* out_proofs);
 
+/* ---- verify -------------------------------------------------- */
+/* Replaces snarkjs groth.isValid(verifyingKey, proof, publicSignals) at
+ * operator/src/snarks/common.ts:30-34 with the on-chain predicate of
+ * contracts/contracts/TxVerifier.sol:258-276:
+ *   vk_x = IC[0] + sum input[i] IC[i+1];  e(-A,B) e(alfa1,beta2) e(vk_x,gamma2) e(C,delta2) == 1.
+ * The l-term MSM for vk_x runs on ctx's GPU over IC tables kept resident per verifying key; the
+ * 4-pairing product runs on the calling host thread (O(1) work, ~2 ms).
+ * zkr_vkey_load_json: text of a snarkjs verification_key.json.
+ * zkr_vkey_load_bin:  alfa1|beta1|delta1 (64 B each) | beta2|gamma2|delta2 (128 B each) | IC[0..l]
+ *                     (64 B each), Fq-M -- the vk block zkr_synth_setup emits.
+ * Both validate every point (on curve; G2 in the order-r subgroup) -> ZKR_E_BADKEY otherwise. */
+typedef struct zkr_vkey zkr_vkey;
+int zkr_vkey_load_json(zkr_ctx* ctx, const char* json, size_t len, zkr_vkey** out);
+int zkr_vkey_load_bin(zkr_ctx* ctx, const void* buf, size_t len, zkr_vkey** out);
+void zkr_vkey_free(zkr_vkey* vk);
+int zkr_vkey_info(const zkr_vkey* vk, uint32_t* n_public);
+/* proof: 256 B in zkr_prove's output encoding.  public_signals: n_public x 32 B std form, HOST memory.
+ * *valid = 1 iff the predicate holds; malformed proof points (coordinate >= q, off curve, B outside the
+ * subgroup) give *valid = 0.  Errors mirror the contract's reverts: n_public != nPublic of the key ->
+ * ZKR_E_INVALID ("verifier-bad-input", TxVerifier.sol:261); a signal >= r -> ZKR_E_WITNESS_RANGE
+ * ("verifier-gte-snark-scalar-field", :265). */
+int zkr_verify(zkr_ctx* ctx, const zkr_vkey* vk, const void* proof, const void* public_signals,
+               size_t n_public, int* valid);
+/* prod_i e(P_i, Q_i) == 1 for n <= 8 pairs; g1_points n x 64 B, g2_points n x 128 B (x.c0|x.c1|y.c0|y.c1),
+ * std form affine, all-zero = infinity: the alt_bn128 pairing-check TxVerifier.sol:91-116 calls.
+ * Host-only.  Invalid inputs (>= q, off curve, G2 outside the subgroup) -> ZKR_E_INVALID, like the
+ * precompile failing. */
+int zkr_pairing_check(const void* g1_points, const void* g2_points, size_t n, int* is_one);
+
 /* ---- standalone MSM ----------------------------------------------------------------- */
 /* group: 1 = G1 (64 B affine Fq-M points), 2 = G2 (128 B, x.c0|x.c1|y.c0|y.c1).
  * points: host memory, n of them; x == 0 marks infinity (skipped).  Builds the windowed

@@ -56,6 +56,12 @@ _SIGS = {
     "zkr_witness_json_to_bin": (C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "zkr_buf_free": (None, [C.c_void_p]),
     "zkr_pkey_load_json": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "zkr_vkey_load_json": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "zkr_vkey_load_bin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "zkr_vkey_free": (None, [C.c_void_p]),
+    "zkr_vkey_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32)]),
+    "zkr_verify": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int)]),
+    "zkr_pairing_check": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int)]),
     "zkr_prove": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
                             C.c_void_p, C.POINTER(Stats)]),
     "zkr_prove_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,

@@ -14,6 +14,7 @@
 #include <new>
 
 #include "common.cuh"
+#include "keyjson_iface.cuh"
 
 namespace zkr {
 namespace {
@@ -378,6 +379,83 @@ int bad(const Reader& r) {
 
 }  // namespace
 }  // namespace zkr
+
+int zkr::vkey_parse_json(const char* json, size_t len, VKeyRaw* out) {
+    Reader r;
+    r.p = r.begin = json;
+    r.end = json + len;
+    r.msg[0] = 0;
+    auto bad_vk = [&]() {
+        set_error("verification key JSON: %s", r.msg);
+        return ZKR_E_BADKEY;
+    };
+    bool have[6] = {false, false, false, false, false, false};   // nPublic, IC, alfa1, beta2, gamma2, delta2
+    uint64_t n_ic = 0;
+    try {
+        if (!r.eat('{')) {
+            r.fail("expected '{'");
+            return bad_vk();
+        }
+        if (!r.eat('}')) {
+            for (;;) {
+                const char* ks;
+                size_t kn;
+                if (!r.string(ks, kn)) return bad_vk();
+                if (!r.eat(':')) {
+                    r.fail("expected ':'");
+                    return bad_vk();
+                }
+                auto is = [&](const char* name) { return kn == strlen(name) && memcmp(ks, name, kn) == 0; };
+                if (is("nPublic")) {
+                    if (!r.u32(out->n_public)) return bad_vk();
+                    have[0] = true;
+                } else if (is("IC")) {
+                    uint64_t nulls = 0;
+                    out->ic.clear();
+                    if (!point_array(r, 1, out->ic, n_ic, nulls)) return bad_vk();
+                    if (nulls) {
+                        r.fail("null point in IC");
+                        return bad_vk();
+                    }
+                    have[1] = true;
+                } else if (is("vk_alfa_1")) {
+                    if (!g1_point(r, out->alfa1)) return bad_vk();
+                    have[2] = true;
+                } else if (is("vk_beta_2")) {
+                    if (!g2_point(r, out->beta2)) return bad_vk();
+                    have[3] = true;
+                } else if (is("vk_gamma_2")) {
+                    if (!g2_point(r, out->gamma2)) return bad_vk();
+                    have[4] = true;
+                } else if (is("vk_delta_2")) {
+                    if (!g2_point(r, out->delta2)) return bad_vk();
+                    have[5] = true;
+                } else if (!r.skip_value()) {
+                    return bad_vk();
+                }
+                if (r.eat(',')) continue;
+                if (r.eat('}')) break;
+                r.fail("malformed object");
+                return bad_vk();
+            }
+        }
+    } catch (const std::bad_alloc&) {
+        set_error("out of host memory while parsing the verification key JSON");
+        return ZKR_E_NOMEM;
+    }
+    static const char* const names[6] = {"nPublic", "IC", "vk_alfa_1", "vk_beta_2", "vk_gamma_2", "vk_delta_2"};
+    for (int i = 0; i < 6; i++)
+        if (!have[i]) {
+            set_error("verification key JSON: field %s missing", names[i]);
+            return ZKR_E_BADKEY;
+        }
+    if (n_ic != (uint64_t)out->n_public + 1) {
+        set_error("verification key JSON: IC has %llu entries, nPublic + 1 = %llu expected", (unsigned long long)n_ic,
+                  (unsigned long long)out->n_public + 1);
+        return ZKR_E_BADKEY;
+    }
+    return ZKR_OK;
+}
 
 using namespace zkr;
 

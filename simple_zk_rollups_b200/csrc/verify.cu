@@ -1,0 +1,678 @@
+// Groth16 verification for the proof generator's self-check.
+//
+// Replaces snarkjs `groth.isValid(verifyingKey, proof, publicSignals)` at
+// /root/reference/operator/src/snarks/common.ts:30-34, which the reference runs after EVERY proof on the JS
+// BigInt path (seconds) and which would dominate createProofGenerator once the prove itself takes milliseconds.
+// The predicate is the on-chain one, /root/reference/contracts/contracts/TxVerifier.sol:258-276:
+//     vk_x = IC[0] + sum_i input[i] * IC[i+1]                       (inputs < r, :265)
+//     e(-A, B) * e(alfa1, beta2) * e(vk_x, gamma2) * e(C, delta2) == 1   (pairingProd4, :269-274)
+// Split of work:
+//   * vk_x is an l-term G1 MSM over bases fixed per circuit (l = 73 for tx.circom, 577 / 2305 at the scaled
+//     sizes): it runs on the GPU through the same window-precomputed bucket MSM as the prover (zkr_bases_load
+//     once per verifying key, zkr_msm per proof) -- on the host it would cost l double-and-add multiplications.
+//   * the pairing product is O(1) work with no data parallelism (4 Miller loops sharing one accumulator, one
+//     final exponentiation): it runs on the host core that issued the call, 4 x 64-bit Montgomery limbs,
+//     ~2 ms, while the GPU is free for the next proof.  Same split as the reference (pairings on the CPU).
+// Fq12 = Fq2[w]/(w^6 - xi), xi = 9 + u; optimal-ate Miller loop over 6x+2 with affine twist points (the
+// inversions of all pairs are batched per step), two Frobenius line additions, final exponentiation with the
+// BN hard part of Scott et al. (exponentiations by x, Frobenius maps).
+#include <cstring>
+
+#include "common.cuh"
+#include "keyjson_iface.cuh"
+
+namespace zkr {
+namespace pr {
+
+typedef unsigned __int128 u128;
+
+// ------------------------------------------------------------------------------------------------ Fq
+struct Fq {
+    uint64_t v[4];
+};
+const uint64_t kP[4] = {0x3c208c16d87cfd47ull, 0x97816a916871ca8dull, 0xb85045b68181585dull, 0x30644e72e131a029ull};
+const uint64_t kInv = 0x87d20782e4866389ull;
+const Fq kOne = {{0xd35d438dc58f0d9dull, 0x0a78eb28f5c70b3dull, 0x666ea36f7879462cull, 0x0e0a77c19a07df2full}};
+const Fq kR2 = {{0xf32cfc5b538afa89ull, 0xb5e71911d44501fbull, 0x47ab1eff0a417ff6ull, 0x06d89f71cab8351full}};
+const Fq kZero = {{0, 0, 0, 0}};
+// scalar field modulus r (TxVerifier.sol:259), for the G2 subgroup check
+const uint64_t kRmod[4] = {0x43e1f593f0000001ull, 0x2833e84879b97091ull, 0xb85045b68181585dull, 0x30644e72e131a029ull};
+
+inline bool is_zero(const Fq& a) { return (a.v[0] | a.v[1] | a.v[2] | a.v[3]) == 0; }
+inline bool eq(const Fq& a, const Fq& b) {
+    return ((a.v[0] ^ b.v[0]) | (a.v[1] ^ b.v[1]) | (a.v[2] ^ b.v[2]) | (a.v[3] ^ b.v[3])) == 0;
+}
+inline bool geq_p(const uint64_t* a) {
+    for (int i = 3; i >= 0; i--)
+        if (a[i] != kP[i]) return a[i] > kP[i];
+    return true;
+}
+inline Fq add(const Fq& a, const Fq& b) {
+    Fq r;
+    u128 c = 0;
+    for (int i = 0; i < 4; i++) {
+        c += (u128)a.v[i] + b.v[i];
+        r.v[i] = (uint64_t)c;
+        c >>= 64;
+    }
+    if (geq_p(r.v)) {      // a + b < 2p < 2^255: no carry out
+        u128 bw = 0;
+        for (int i = 0; i < 4; i++) {
+            u128 d = (u128)r.v[i] - kP[i] - (uint64_t)bw;
+            r.v[i] = (uint64_t)d;
+            bw = (d >> 64) & 1;
+        }
+    }
+    return r;
+}
+inline Fq sub(const Fq& a, const Fq& b) {
+    Fq r;
+    u128 bw = 0;
+    for (int i = 0; i < 4; i++) {
+        u128 d = (u128)a.v[i] - b.v[i] - (uint64_t)bw;
+        r.v[i] = (uint64_t)d;
+        bw = (d >> 64) & 1;
+    }
+    if (bw) {
+        u128 c = 0;
+        for (int i = 0; i < 4; i++) {
+            c += (u128)r.v[i] + kP[i];
+            r.v[i] = (uint64_t)c;
+            c >>= 64;
+        }
+    }
+    return r;
+}
+inline Fq neg(const Fq& a) { return is_zero(a) ? a : sub(kZero, a); }
+inline Fq dbl(const Fq& a) { return add(a, a); }
+inline Fq mul(const Fq& a, const Fq& b) {
+    uint64_t t[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 4; i++) {
+        u128 c = 0;
+        for (int j = 0; j < 4; j++) {
+            c += (u128)a.v[j] * b.v[i] + t[j];
+            t[j] = (uint64_t)c;
+            c >>= 64;
+        }
+        c += t[4];
+        t[4] = (uint64_t)c;
+        t[5] = (uint64_t)(c >> 64);
+        const uint64_t k = t[0] * kInv;
+        c = (u128)k * kP[0] + t[0];
+        c >>= 64;
+        for (int j = 1; j < 4; j++) {
+            c += (u128)k * kP[j] + t[j];
+            t[j - 1] = (uint64_t)c;
+            c >>= 64;
+        }
+        c += t[4];
+        t[3] = (uint64_t)c;
+        t[4] = t[5] + (uint64_t)(c >> 64);
+    }
+    Fq r = {{t[0], t[1], t[2], t[3]}};
+    if (t[4] || geq_p(r.v)) {
+        u128 bw = 0;
+        for (int i = 0; i < 4; i++) {
+            u128 d = (u128)r.v[i] - kP[i] - (uint64_t)bw;
+            r.v[i] = (uint64_t)d;
+            bw = (d >> 64) & 1;
+        }
+    }
+    return r;
+}
+inline Fq sqr(const Fq& a) { return mul(a, a); }
+inline Fq inv(const Fq& a) {    // a^(p-2)
+    uint64_t e[4] = {kP[0] - 2, kP[1], kP[2], kP[3]};
+    Fq acc = kOne, base = a;
+    for (int i = 0; i < 254; i++) {
+        if ((e[i >> 6] >> (i & 63)) & 1) acc = mul(acc, base);
+        base = sqr(base);
+    }
+    return acc;
+}
+// 32 B little-endian standard form -> Montgomery; false if >= q
+inline bool from_std(const uint8_t* b, Fq& out) {
+    Fq s;
+    memcpy(s.v, b, 32);
+    if (geq_p(s.v)) return false;
+    out = mul(s, kR2);
+    return true;
+}
+inline Fq from_mont_bytes(const uint8_t* b) {
+    Fq s;
+    memcpy(s.v, b, 32);
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------------ Fq2
+struct Fq2 {
+    Fq c0, c1;
+};
+const Fq2 kZero2 = {kZero, kZero};
+const Fq2 kOne2 = {kOne, kZero};
+inline bool is_zero(const Fq2& a) { return is_zero(a.c0) && is_zero(a.c1); }
+inline bool eq(const Fq2& a, const Fq2& b) { return eq(a.c0, b.c0) && eq(a.c1, b.c1); }
+inline Fq2 add(const Fq2& a, const Fq2& b) { return {add(a.c0, b.c0), add(a.c1, b.c1)}; }
+inline Fq2 sub(const Fq2& a, const Fq2& b) { return {sub(a.c0, b.c0), sub(a.c1, b.c1)}; }
+inline Fq2 neg(const Fq2& a) { return {neg(a.c0), neg(a.c1)}; }
+inline Fq2 dbl(const Fq2& a) { return {dbl(a.c0), dbl(a.c1)}; }
+inline Fq2 conj(const Fq2& a) { return {a.c0, neg(a.c1)}; }
+inline Fq2 mul(const Fq2& a, const Fq2& b) {
+    Fq t0 = mul(a.c0, b.c0), t1 = mul(a.c1, b.c1);
+    Fq t2 = mul(add(a.c0, a.c1), add(b.c0, b.c1));
+    return {sub(t0, t1), sub(sub(t2, t0), t1)};
+}
+inline Fq2 sqr(const Fq2& a) {
+    Fq t = mul(a.c0, a.c1);
+    return {mul(add(a.c0, a.c1), sub(a.c0, a.c1)), dbl(t)};
+}
+inline Fq2 mul_fq(const Fq2& a, const Fq& k) { return {mul(a.c0, k), mul(a.c1, k)}; }
+inline Fq2 inv(const Fq2& a) {
+    Fq n = inv(add(sqr(a.c0), sqr(a.c1)));
+    return {mul(a.c0, n), neg(mul(a.c1, n))};
+}
+inline Fq2 mul_xi(const Fq2& a) {    // (9 + u)(c0 + c1 u) = (9 c0 - c1) + (9 c1 + c0) u
+    Fq n0 = add(dbl(dbl(dbl(a.c0))), a.c0), n1 = add(dbl(dbl(dbl(a.c1))), a.c1);
+    return {sub(n0, a.c1), add(n1, a.c0)};
+}
+inline Fq2 fq2_from_u64(const uint64_t (*c)[4]) {
+    Fq2 r;
+    memcpy(r.c0.v, c[0], 32);
+    memcpy(r.c1.v, c[1], 32);
+    return r;
+}
+
+// gamma[k-1][i-1] = xi^(i (q^k - 1)/6), Montgomery form (generated with the oracle's Fq2 arithmetic;
+// cross-checked by tests/test_verify.py through Frobenius consistency of the pairing itself)
+const uint64_t kGamma[3][5][2][4] = {
+    {
+        {{0xaf9ba69633144907ull, 0xca6b1d7387afb78aull, 0x11bded5ef08a2087ull, 0x02f34d751a1f3a7cull},
+         {0xa222ae234c492d72ull, 0xd00f02a4565de15bull, 0xdc2ff3a253dfc926ull, 0x10a75716b3899551ull}},
+        {{0xb5773b104563ab30ull, 0x347f91c8a9aa6454ull, 0x7a007127242e0991ull, 0x1956bcd8118214ecull},
+         {0x6e849f1ea0aa4757ull, 0xaa1c7b6d89f89141ull, 0xb6e713cdfae0ca3aull, 0x26694fbb4e82ebc3ull}},
+        {{0xe4bbdd0c2936b629ull, 0xbb30f162e133bacbull, 0x31a9d1b6f9645366ull, 0x253570bea500f8ddull},
+         {0xa1d77ce45ffe77c7ull, 0x07affd117826d1dbull, 0x6d16bd27bb7edc6bull, 0x2c87200285defeccull}},
+        {{0x7361d77f843abe92ull, 0xa5bb2bd3273411fbull, 0x9c941f314b3e2399ull, 0x15df9cddbb9fd3ecull},
+         {0x5dddfd154bd8c949ull, 0x62cb29a5a4445b60ull, 0x37bc870a0c7dd2b9ull, 0x24830a9d3171f0fdull}},
+        {{0xc970692f41690fe7ull, 0xe240342127694b0bull, 0x32bee66b83c459e8ull, 0x12aabced0ab08841ull},
+         {0x0d485d2340aebfa9ull, 0x05193418ab2fcc57ull, 0xd3b0a40b8a4910f5ull, 0x2f21ebb535d2925aull}},
+    },
+    {
+        {{0xca8d800500fa1bf2ull, 0xf0c5d61468b39769ull, 0x0e201271ad0d4418ull, 0x04290f65bad856e6ull}, {0, 0, 0, 0}},
+        {{0x3350c88e13e80b9cull, 0x7dce557cdb5e56b9ull, 0x6001b4b8b615564aull, 0x2682e617020217e0ull}, {0, 0, 0, 0}},
+        {{0x68c3488912edefaaull, 0x8d087f6872aabf4full, 0x51e1a24709081231ull, 0x2259d6b14729c0faull}, {0, 0, 0, 0}},
+        {{0x71930c11d782e155ull, 0xa6bb947cffbe3323ull, 0xaa303344d4741444ull, 0x2c3b3f0d26594943ull}, {0, 0, 0, 0}},
+        {{0x08cfc388c494f1abull, 0x19b315148d1373d4ull, 0x584e90fdcb6c0213ull, 0x09e1685bdf2f8849ull}, {0, 0, 0, 0}},
+    },
+    {
+        {{0x365316184e46d97dull, 0x0af7129ed4c96d9full, 0x659da72fca1009b5ull, 0x08116d8983a20d23ull},
+         {0xb1df4af7c39c1939ull, 0x3d9f02878a73bf7full, 0x9b2220928caf0ae0ull, 0x26684515eff054a6ull}},
+        {{0xc9af22f716ad6badull, 0xb311782a4aa662b2ull, 0x19eeaf64e248c7f4ull, 0x20273e77e3439f82ull},
+         {0xacc02860f7ce93acull, 0x3933d5817ba76b4cull, 0x69e6188b446c8467ull, 0x0a46036d4417cc55ull}},
+        {{0x5764af0aaf46471eull, 0xdc50792e873e0fc1ull, 0x86a673ff881d04f6ull, 0x0b2eddb43c30a74cull},
+         {0x9a490f32787e8580ull, 0x8fd16d7ff04af8b1ull, 0x4b39888ec6027bf2ull, 0x03dd2e705b52a15dull}},
+        {{0x448a93a57b6762dfull, 0xbfd62df528fdeadfull, 0xd858f5d00e9bd47aull, 0x06b03d4d3476ec58ull},
+         {0x2b19daf4bcc936d1ull, 0xa1a54e7a56f4299full, 0xb533eee05adeaef1ull, 0x170c812b84dda0b2ull}},
+        {{0xe0bc4b2275cf559full, 0xc238b945c154e60full, 0x803982a5929a7d5eull, 0x15ce052df7e4a37eull},
+         {0x2d28efbdbf3799a7ull, 0x9b097e3c1ad60773ull, 0x982d4113af4a535bull, 0x24e18991e3056063ull}},
+    },
+};
+// twist coefficient b' = 3 / (9 + u), Montgomery (TxVerifier.sol's precompile curve: y^2 = x^3 + 3/(9+u))
+const uint64_t kTwistB[2][4] = {{0x3bf938e377b802a8ull, 0x020b1b273633535dull, 0x26b7edf049755260ull, 0x2514c6324384a86dull},
+                                {0x38e7ecccd1dcff67ull, 0x65f0b37d93ce0d3eull, 0xd749d0dd22ac00aaull, 0x0141b9ce4a688d4dull}};
+const Fq kThree = {{0x7a17caa950ad28d7ull, 0x1f6ac17ae15521b9ull, 0x334bea4e696bd284ull, 0x2a1f6744ce179d8eull}};
+const uint64_t kBnX = 4965661367192848881ull;                         // BN parameter x
+const u128 kAteLoop = ((u128)0x1ull << 64) | 0x9d797039be763ba8ull;   // 6x + 2 = 29793968203157093288 (65 bits)
+
+inline Fq2 gamma(int k, int i) { return fq2_from_u64(kGamma[k - 1][i - 1]); }
+
+// ------------------------------------------------------------------------------------------------ Fq12
+struct Fq12 {
+    Fq2 c[6];      // sum c[i] w^i, w^6 = xi
+};
+inline Fq12 f12_one() {
+    Fq12 r;
+    r.c[0] = kOne2;
+    for (int i = 1; i < 6; i++) r.c[i] = kZero2;
+    return r;
+}
+inline bool f12_is_one(const Fq12& a) {
+    if (!eq(a.c[0], kOne2)) return false;
+    for (int i = 1; i < 6; i++)
+        if (!is_zero(a.c[i])) return false;
+    return true;
+}
+Fq12 f12_mul(const Fq12& a, const Fq12& b) {
+    Fq2 t[11];
+    for (int i = 0; i < 11; i++) t[i] = kZero2;
+    for (int i = 0; i < 6; i++)
+        for (int j = 0; j < 6; j++) t[i + j] = add(t[i + j], mul(a.c[i], b.c[j]));
+    Fq12 r;
+    for (int k = 0; k < 6; k++) r.c[k] = k < 5 ? add(t[k], mul_xi(t[k + 6])) : t[k];
+    return r;
+}
+inline Fq12 f12_sqr(const Fq12& a) { return f12_mul(a, a); }
+// a * (l0 + l1 w + l3 w^3), l0 in Fq
+Fq12 f12_mul_line(const Fq12& a, const Fq& l0, const Fq2& l1, const Fq2& l3) {
+    Fq2 t[9];
+    for (int i = 0; i < 9; i++) t[i] = kZero2;
+    for (int i = 0; i < 6; i++) {
+        t[i] = add(t[i], mul_fq(a.c[i], l0));
+        t[i + 1] = add(t[i + 1], mul(a.c[i], l1));
+        t[i + 3] = add(t[i + 3], mul(a.c[i], l3));
+    }
+    Fq12 r;
+    for (int k = 0; k < 6; k++) r.c[k] = k < 3 ? add(t[k], mul_xi(t[k + 6])) : t[k];
+    return r;
+}
+inline Fq12 f12_conj(const Fq12& a) {       // the q^6 Frobenius: w -> -w
+    Fq12 r = a;
+    r.c[1] = neg(a.c[1]);
+    r.c[3] = neg(a.c[3]);
+    r.c[5] = neg(a.c[5]);
+    return r;
+}
+// a^(q^k), k = 1, 2, 3:  (c_i w^i)^(q^k) = conj^k(c_i) gamma_k^i w^i
+Fq12 f12_frob(const Fq12& a, int k) {
+    Fq12 r;
+    for (int i = 0; i < 6; i++) {
+        Fq2 c = (k & 1) ? conj(a.c[i]) : a.c[i];
+        r.c[i] = i == 0 ? c : mul(c, gamma(k, i));
+    }
+    return r;
+}
+// inverse through the norm to Fq:  a^-1 = a^(q + q^2 + ... + q^11) / N(a)
+Fq12 f12_inv(const Fq12& a) {
+    Fq12 s1 = f12_frob(a, 1);                                    // a^q
+    Fq12 s2 = f12_mul(s1, f12_frob(s1, 1));                      // a^(q + q^2)
+    Fq12 s3 = f12_mul(s2, f12_frob(s1, 2));                      // a^(q + q^2 + q^3)
+    Fq12 s4 = f12_mul(s2, f12_frob(s2, 2));                      // a^(q + .. + q^4)
+    Fq12 s8 = f12_mul(s4, f12_frob(f12_frob(s4, 2), 2));         // a^(q + .. + q^8)
+    Fq12 t = s3;
+    for (int i = 0; i < 4; i++) t = f12_frob(t, 2);              // a^(q^9 + q^10 + q^11)
+    Fq12 rr = f12_mul(s8, t);                                    // a^(q + .. + q^11)
+    Fq12 n = f12_mul(a, rr);                                     // norm, lies in Fq
+    Fq ninv = inv(n.c[0].c0);
+    Fq12 out;
+    for (int i = 0; i < 6; i++) out.c[i] = mul_fq(rr.c[i], ninv);
+    return out;
+}
+Fq12 f12_exp_x(const Fq12& a) {
+    Fq12 r = a;
+    for (int i = 61; i >= 0; i--) {       // kBnX has 63 bits, top bit consumed by r = a
+        r = f12_sqr(r);
+        if ((kBnX >> i) & 1) r = f12_mul(r, a);
+    }
+    return r;
+}
+// f^((q^12 - 1) / r): easy part (q^6 - 1)(q^2 + 1), hard part of Scott, Benger, Charlemagne, Dominguez Perez,
+// Kachisa, "On the final exponentiation for calculating pairings on ordinary elliptic curves" (BN case)
+Fq12 final_exp(const Fq12& in) {
+    Fq12 t1 = f12_mul(f12_conj(in), f12_inv(in));
+    t1 = f12_mul(f12_frob(t1, 2), t1);
+    Fq12 fp = f12_frob(t1, 1), fp2 = f12_frob(t1, 2), fp3 = f12_frob(fp2, 1);
+    Fq12 fu = f12_exp_x(t1), fu2 = f12_exp_x(fu), fu3 = f12_exp_x(fu2);
+    Fq12 y3 = f12_conj(f12_frob(fu, 1));
+    Fq12 fu2p = f12_frob(fu2, 1), fu3p = f12_frob(fu3, 1);
+    Fq12 y2 = f12_frob(fu2, 2);
+    Fq12 y0 = f12_mul(f12_mul(fp, fp2), fp3);
+    Fq12 y1 = f12_conj(t1);
+    Fq12 y5 = f12_conj(fu2);
+    Fq12 y4 = f12_conj(f12_mul(fu, fu2p));
+    Fq12 y6 = f12_conj(f12_mul(fu3, fu3p));
+    Fq12 t0 = f12_mul(f12_mul(f12_sqr(y6), y4), y5);
+    Fq12 u1 = f12_mul(f12_mul(y3, y5), t0);
+    t0 = f12_mul(t0, y2);
+    u1 = f12_sqr(f12_mul(f12_sqr(u1), t0));
+    t0 = f12_mul(u1, y1);
+    u1 = f12_mul(u1, y0);
+    t0 = f12_sqr(t0);
+    return f12_mul(t0, u1);
+}
+
+// ------------------------------------------------------------------------------------------------ curves
+struct G1A {
+    Fq x, y;
+    bool inf;
+};
+struct G2A {
+    Fq2 x, y;
+    bool inf;
+};
+inline bool on_curve(const G1A& p) { return p.inf || eq(sqr(p.y), add(mul(sqr(p.x), p.x), kThree)); }
+inline bool on_curve(const G2A& p) {
+    return p.inf || eq(sqr(p.y), add(mul(sqr(p.x), p.x), fq2_from_u64(kTwistB)));
+}
+
+// Jacobian arithmetic, generic over Fq / Fq2 (only for the subgroup check and vk_x = IC[0] + msm)
+template <class F>
+struct Jac {
+    F x, y, z;
+    bool inf;
+};
+template <class F>
+Jac<F> jdbl(const Jac<F>& p) {
+    if (p.inf || is_zero(p.y)) return {p.x, p.y, p.z, true};
+    F a = sqr(p.x), b = sqr(p.y), c = sqr(b);
+    F d = dbl(sub(sub(sqr(add(p.x, b)), a), c));
+    F e = add(dbl(a), a), f = sqr(e);
+    F x3 = sub(f, dbl(d));
+    F y3 = sub(mul(e, sub(d, x3)), dbl(dbl(dbl(c))));
+    F z3 = dbl(mul(p.y, p.z));
+    return {x3, y3, z3, false};
+}
+template <class F>
+Jac<F> jadd_affine(const Jac<F>& p, const F& qx, const F& qy, const F& one) {
+    if (p.inf) return {qx, qy, one, false};
+    F z1z1 = sqr(p.z);
+    F u2 = mul(qx, z1z1), s2 = mul(mul(qy, p.z), z1z1);
+    F h = sub(u2, p.x), rr = sub(s2, p.y);
+    if (is_zero(h)) {
+        if (is_zero(rr)) return jdbl(p);
+        return {p.x, p.y, p.z, true};
+    }
+    F hh = sqr(h), hhh = mul(h, hh), v = mul(p.x, hh);
+    F x3 = sub(sub(sqr(rr), hhh), dbl(v));
+    F y3 = sub(mul(rr, sub(v, x3)), mul(p.y, hhh));
+    F z3 = mul(p.z, h);
+    return {x3, y3, z3, false};
+}
+// [r] Q == O ?   (the alt_bn128 pairing precompile rejects G2 points outside the order-r subgroup)
+bool g2_in_subgroup(const G2A& q) {
+    if (q.inf) return true;
+    Jac<Fq2> acc = {q.x, q.y, kOne2, true};
+    for (int i = 253; i >= 0; i--) {
+        acc = jdbl(acc);
+        if ((kRmod[i >> 6] >> (i & 63)) & 1) acc = jadd_affine(acc, q.x, q.y, kOne2);
+    }
+    return acc.inf;
+}
+G1A g1_add(const G1A& a, const G1A& b) {
+    if (a.inf) return b;
+    if (b.inf) return a;
+    Jac<Fq> j = jadd_affine<Fq>({a.x, a.y, kOne, false}, b.x, b.y, kOne);
+    if (j.inf) return {kZero, kZero, true};
+    Fq zi = inv(j.z), zi2 = sqr(zi);
+    return {mul(j.x, zi2), mul(j.y, mul(zi2, zi)), false};
+}
+
+// ------------------------------------------------------------------------------------------------ pairing
+struct MillerState {
+    Fq2 tx, ty;        // running twist point T (affine)
+    Fq2 qx, qy;        // Q
+    Fq px, py;         // P
+};
+
+// batch inversion (Montgomery's trick); returns false if some element is zero
+bool batch_inv(Fq2* d, int n) {
+    if (n == 0) return true;
+    Fq2 pref[8];
+    Fq2 acc = kOne2;
+    for (int i = 0; i < n; i++) {
+        if (is_zero(d[i])) return false;
+        pref[i] = acc;
+        acc = mul(acc, d[i]);
+    }
+    Fq2 ia = inv(acc);
+    for (int i = n - 1; i >= 0; i--) {
+        Fq2 di = mul(ia, pref[i]);
+        ia = mul(ia, d[i]);
+        d[i] = di;
+    }
+    return true;
+}
+
+// one line step for every pair: T <- T + S (S = T for a doubling, else the given point), f <- f * l_{T,S}(P).
+// Untwist psi(x, y) = (x w^2, y w^3):  l(P) = yP - lambda xP w + (lambda x1 - y1) w^3.
+bool line_step(Fq12& f, MillerState* st, int n, bool doubling, const Fq2* sx, const Fq2* sy) {
+    Fq2 den[8];
+    for (int i = 0; i < n; i++) den[i] = doubling ? dbl(st[i].ty) : sub(sx[i], st[i].tx);
+    if (!batch_inv(den, n)) return false;       // cannot happen for points of order r (see header of zkr_pairing_check)
+    for (int i = 0; i < n; i++) {
+        MillerState& s = st[i];
+        Fq2 lam;
+        if (doubling) {
+            Fq2 x2 = sqr(s.tx);
+            lam = mul(add(dbl(x2), x2), den[i]);
+        } else {
+            lam = mul(sub(sy[i], s.ty), den[i]);
+        }
+        const Fq2& ox = doubling ? s.tx : sx[i];
+        Fq2 x3 = sub(sub(sqr(lam), s.tx), ox);
+        Fq2 y3 = sub(mul(lam, sub(s.tx, x3)), s.ty);
+        Fq2 l1 = neg(mul_fq(lam, s.px));
+        Fq2 l3 = sub(mul(lam, s.tx), s.ty);
+        f = f12_mul_line(f, s.py, l1, l3);
+        s.tx = x3;
+        s.ty = y3;
+    }
+    return true;
+}
+
+// prod_i e(P_i, Q_i) == 1 ?   ok=false: a degenerate line was hit (inputs outside the prime-order groups)
+bool pairing_product_is_one(const G1A* P, const G2A* Q, int n_in, bool* ok) {
+    MillerState st[8];
+    int n = 0;
+    for (int i = 0; i < n_in; i++) {
+        if (P[i].inf || Q[i].inf) continue;       // e(O, Q) = e(P, O) = 1
+        st[n++] = {Q[i].x, Q[i].y, Q[i].x, Q[i].y, P[i].x, P[i].y};
+    }
+    *ok = true;
+    Fq12 f = f12_one();
+    if (n) {
+        Fq2 qx[8], qy[8];
+        for (int i = 0; i < n; i++) {
+            qx[i] = st[i].qx;
+            qy[i] = st[i].qy;
+        }
+        for (int b = 63; b >= 0; b--) {           // bits below the leading one of the 65-bit loop count
+            f = f12_sqr(f);
+            if (!line_step(f, st, n, true, nullptr, nullptr)) return *ok = false;
+            if ((kAteLoop >> b) & 1)
+                if (!line_step(f, st, n, false, qx, qy)) return *ok = false;
+        }
+        // Q1 = pi(Q), -Q2 = -pi^2(Q) on the twist
+        Fq2 g12 = gamma(1, 2), g13 = gamma(1, 3), g22 = gamma(2, 2), g23 = gamma(2, 3);
+        Fq2 ax[8], ay[8];
+        for (int i = 0; i < n; i++) {
+            ax[i] = mul(conj(qx[i]), g12);
+            ay[i] = mul(conj(qy[i]), g13);
+        }
+        if (!line_step(f, st, n, false, ax, ay)) return *ok = false;
+        for (int i = 0; i < n; i++) {
+            ax[i] = mul(qx[i], g22);
+            ay[i] = neg(mul(qy[i], g23));
+        }
+        if (!line_step(f, st, n, false, ax, ay)) return *ok = false;
+    }
+    return f12_is_one(final_exp(f));
+}
+
+// ------------------------------------------------------------------------------------------------ decoding
+// x|y standard form, all-zero = infinity (zkr.h proof encoding; also the EVM's encoding of the zero point)
+bool g1_from_std(const uint8_t* b, G1A& p) {
+    bool z = true;
+    for (int i = 0; i < 64; i++) z &= b[i] == 0;
+    if (z) {
+        p = {kZero, kZero, true};
+        return true;
+    }
+    p.inf = false;
+    return from_std(b, p.x) && from_std(b + 32, p.y);
+}
+bool g2_from_std(const uint8_t* b, G2A& p) {
+    bool z = true;
+    for (int i = 0; i < 128; i++) z &= b[i] == 0;
+    if (z) {
+        p = {kZero2, kZero2, true};
+        return true;
+    }
+    p.inf = false;
+    return from_std(b, p.x.c0) && from_std(b + 32, p.x.c1) && from_std(b + 64, p.y.c0) && from_std(b + 96, p.y.c1);
+}
+// Montgomery bytes (binary key encoding); x == 0 marks infinity (binarify.ts:92-95 drops z)
+G1A g1_from_mont(const uint8_t* b) {
+    G1A p = {from_mont_bytes(b), from_mont_bytes(b + 32), false};
+    p.inf = is_zero(p.x);
+    return p;
+}
+G2A g2_from_mont(const uint8_t* b) {
+    G2A p = {{from_mont_bytes(b), from_mont_bytes(b + 32)}, {from_mont_bytes(b + 64), from_mont_bytes(b + 96)}, false};
+    p.inf = is_zero(p.x);
+    return p;
+}
+
+}  // namespace pr
+}  // namespace zkr
+
+using namespace zkr;
+
+struct zkr_vkey {
+    zkr_ctx* ctx = nullptr;
+    uint32_t n_public = 0;
+    pr::G1A ic0, alfa1;
+    pr::G2A beta2, gamma2, delta2;
+    zkr_bases* ic_bases = nullptr;      // IC[1..n_public], window tables resident in HBM
+};
+
+static int vkey_finish(zkr_ctx* ctx, const VKeyRaw& raw, zkr_vkey** out) {
+    zkr_vkey* vk = new zkr_vkey();
+    vk->ctx = ctx;
+    vk->n_public = raw.n_public;
+    vk->alfa1 = pr::g1_from_mont(raw.alfa1);
+    vk->beta2 = pr::g2_from_mont(raw.beta2);
+    vk->gamma2 = pr::g2_from_mont(raw.gamma2);
+    vk->delta2 = pr::g2_from_mont(raw.delta2);
+    vk->ic0 = pr::g1_from_mont(raw.ic.data());
+    bool good = pr::on_curve(vk->alfa1) && pr::on_curve(vk->ic0);
+    for (uint32_t i = 1; good && i <= raw.n_public; i++) good = pr::on_curve(pr::g1_from_mont(raw.ic.data() + 64 * (size_t)i));
+    const pr::G2A* g2s[3] = {&vk->beta2, &vk->gamma2, &vk->delta2};
+    for (int i = 0; good && i < 3; i++) good = pr::on_curve(*g2s[i]) && pr::g2_in_subgroup(*g2s[i]);
+    if (!good) {
+        delete vk;
+        set_error("verification key: a point is not on the curve / not in the order-r subgroup");
+        return ZKR_E_BADKEY;
+    }
+    if (raw.n_public) {
+        int rc = zkr_bases_load(ctx, 1, raw.ic.data() + 64, raw.n_public, 0, &vk->ic_bases);
+        if (rc != ZKR_OK) {
+            delete vk;
+            return rc;
+        }
+    }
+    *out = vk;
+    return ZKR_OK;
+}
+
+extern "C" int zkr_vkey_load_json(zkr_ctx* ctx, const char* json, size_t len, zkr_vkey** out) {
+    if (!ctx || !json || !out) {
+        set_error("zkr_vkey_load_json: null argument");
+        return ZKR_E_INVALID;
+    }
+    *out = nullptr;
+    VKeyRaw raw;
+    ZKR_TRY(vkey_parse_json(json, len, &raw));
+    return vkey_finish(ctx, raw, out);
+}
+
+// buf: alfa1 | beta1 | delta1 (64 B each) | beta2 | gamma2 | delta2 (128 B each) | IC[0..l] (64 B each), Fq-M:
+// the vk block zkr_synth_setup emits
+extern "C" int zkr_vkey_load_bin(zkr_ctx* ctx, const void* buf, size_t len, zkr_vkey** out) {
+    if (!ctx || !buf || !out) {
+        set_error("zkr_vkey_load_bin: null argument");
+        return ZKR_E_INVALID;
+    }
+    *out = nullptr;
+    if (len < 576 + 64 || (len - 576) % 64) {
+        set_error("verification key buffer: length %zu is not 576 + 64 (nPublic + 1)", len);
+        return ZKR_E_BADKEY;
+    }
+    const uint8_t* b = (const uint8_t*)buf;
+    VKeyRaw raw;
+    raw.n_public = (uint32_t)((len - 576) / 64 - 1);
+    memcpy(raw.alfa1, b, 64);
+    memcpy(raw.beta2, b + 192, 128);
+    memcpy(raw.gamma2, b + 320, 128);
+    memcpy(raw.delta2, b + 448, 128);
+    raw.ic.assign(b + 576, b + len);
+    return vkey_finish(ctx, raw, out);
+}
+
+extern "C" void zkr_vkey_free(zkr_vkey* vk) {
+    if (!vk) return;
+    if (vk->ic_bases) zkr_bases_free(vk->ic_bases);
+    delete vk;
+}
+
+extern "C" int zkr_vkey_info(const zkr_vkey* vk, uint32_t* n_public) {
+    if (!vk) return ZKR_E_INVALID;
+    if (n_public) *n_public = vk->n_public;
+    return ZKR_OK;
+}
+
+extern "C" int zkr_verify(zkr_ctx* ctx, const zkr_vkey* vk, const void* proof, const void* public_signals,
+                          size_t n_public, int* valid) {
+    if (!ctx || !vk || !proof || !valid || vk->ctx != ctx || (n_public && !public_signals)) {
+        set_error("zkr_verify: bad arguments");
+        return ZKR_E_INVALID;
+    }
+    *valid = 0;
+    if (n_public != vk->n_public) {      // require(input.length + 1 == vk.IC.length, "verifier-bad-input")  TxVerifier.sol:261
+        set_error("verifier-bad-input: %zu public signals given, the key has %u", n_public, vk->n_public);
+        return ZKR_E_INVALID;
+    }
+    const uint8_t* pb = (const uint8_t*)proof;
+    pr::G1A a, c;
+    pr::G2A b;
+    if (!pr::g1_from_std(pb, a) || !pr::g2_from_std(pb + 64, b) || !pr::g1_from_std(pb + 192, c)) return ZKR_OK;
+    if (!pr::on_curve(a) || !pr::on_curve(b) || !pr::on_curve(c) || !pr::g2_in_subgroup(b)) return ZKR_OK;
+    // vk_x = IC[0] + sum input[i] IC[i+1]: GPU MSM over the resident IC tables (range check input[i] < r inside)
+    pr::G1A vkx = vk->ic0;
+    if (n_public) {
+        uint8_t acc[64];
+        ZKR_TRY(zkr_msm(ctx, vk->ic_bases, public_signals, n_public, 0, acc));
+        pr::G1A s;
+        if (!pr::g1_from_std(acc, s)) {
+            set_error("zkr_verify: MSM result out of range");
+            return ZKR_E_CUDA;
+        }
+        vkx = pr::g1_add(vkx, s);
+    }
+    pr::G1A na = a;
+    if (!na.inf) na.y = pr::neg(na.y);       // Pairing.negate(proof.A), TxVerifier.sol:270
+    const pr::G1A P[4] = {na, vk->alfa1, vkx, c};
+    const pr::G2A Q[4] = {b, vk->beta2, vk->gamma2, vk->delta2};
+    bool ok = true;
+    const bool one = pr::pairing_product_is_one(P, Q, 4, &ok);
+    *valid = (ok && one) ? 1 : 0;
+    return ZKR_OK;
+}
+
+// prod e(P_i, Q_i) == 1 over n <= 8 pairs of standard-form affine points (64 B / 128 B each, all-zero =
+// infinity): the alt_bn128 pairing-check predicate TxVerifier.sol:91-116 hands to precompile 8.  Like the
+// precompile it FAILS (ZKR_E_INVALID) on coordinates >= q, points off the curve, or G2 points outside the
+// order-r subgroup -- which is also what guarantees the Miller loop never meets a degenerate line.  Host-only.
+extern "C" int zkr_pairing_check(const void* g1_points, const void* g2_points, size_t n, int* is_one) {
+    if (!is_one || n > 8 || (n && (!g1_points || !g2_points))) {
+        set_error("zkr_pairing_check: bad arguments (at most 8 pairs)");
+        return ZKR_E_INVALID;
+    }
+    *is_one = 0;
+    pr::G1A P[8];
+    pr::G2A Q[8];
+    for (size_t i = 0; i < n; i++) {
+        if (!pr::g1_from_std((const uint8_t*)g1_points + 64 * i, P[i]) || !pr::g2_from_std((const uint8_t*)g2_points + 128 * i, Q[i]) ||
+            !pr::on_curve(P[i]) || !pr::on_curve(Q[i]) || !pr::g2_in_subgroup(Q[i])) {
+            set_error("zkr_pairing_check: pair %zu is not a valid (G1, G2) input", i);
+            return ZKR_E_INVALID;
+        }
+    }
+    bool ok = true;
+    const bool one = pr::pairing_product_is_one(P, Q, (int)n, &ok);
+    if (!ok) {
+        set_error("zkr_pairing_check: degenerate line (internal)");
+        return ZKR_E_INVALID;
+    }
+    *is_one = one ? 1 : 0;
+    return ZKR_OK;
+}

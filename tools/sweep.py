@@ -53,6 +53,9 @@ def main():
     ap.add_argument("--g2-max-log", type=int, default=22)
     ap.add_argument("--out", default="gpurun_out/sweep.json")
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--min-log", type=int, default=16)
+    ap.add_argument("--g2-min-log", type=int, default=16)
+    ap.add_argument("--skip-ntt", action="store_true")
     args = ap.parse_args()
     L = _lib.lib()
     ctx = C.c_void_p()
@@ -77,7 +80,7 @@ def main():
         return min(ts), float(np.median(ts))
 
     for group, max_log in ((1, args.max_log), (2, min(args.g2_max_log, args.max_log))):
-        for lg in range(16, max_log + 1, 2):
+        for lg in range(args.min_log if group == 1 else args.g2_min_log, max_log + 1, 2):
             n = 1 << lg
             t0 = time.time()
             s64 = rng.integers(1, 1 << 63, size=n, dtype=np.uint64)
@@ -126,7 +129,7 @@ def main():
                 del d_k
             L.zkr_bases_free(bases)
             del pts
-    for lg in range(16, min(args.max_log + 2, 26) + 1, 2):
+    for lg in range(16, (0 if args.skip_ntt else min(args.max_log + 2, 26)) + 1, 2):
         n = 1 << lg
         x = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
         x[:, 31] &= 0x1F
