@@ -86,6 +86,16 @@ def proof_from_bytes(buf):
             "pi_c": [v[6], v[7], "1"], "protocol": "groth"}
 
 
+def proof_to_bytes(proof):
+    """{pi_a, pi_b, pi_c} (decimal strings or ints, SURVEY A.4) -> the 256-byte C-ABI proof encoding;
+    a zero z coordinate (snarkjs affine zero) becomes all-zero coordinates."""
+    a, b, c = proof["pi_a"], proof["pi_b"], proof["pi_c"]
+    g1 = lambda p: [0, 0] if len(p) > 2 and int(p[2]) == 0 else [int(p[0]), int(p[1])]
+    zb = len(b) > 2 and int(b[2][0]) == 0 and int(b[2][1]) == 0
+    vals = g1(a) + ([0, 0, 0, 0] if zb else [int(b[0][0]), int(b[0][1]), int(b[1][0]), int(b[1][1])]) + g1(c)
+    return b"".join(v.to_bytes(32, "little") for v in vals)
+
+
 def _native_json_to_bin(fn_name, text):
     from . import _lib
     L = _lib.lib()

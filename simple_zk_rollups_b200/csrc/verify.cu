@@ -16,6 +16,8 @@
 // Fq12 = Fq2[w]/(w^6 - xi), xi = 9 + u; optimal-ate Miller loop over 6x+2 with affine twist points (the
 // inversions of all pairs are batched per step), two Frobenius line additions, final exponentiation with the
 // BN hard part of Scott et al. (exponentiations by x, Frobenius maps).
+#include <immintrin.h>
+
 #include <cstring>
 
 #include "common.cuh"
@@ -47,78 +49,70 @@ inline bool geq_p(const uint64_t* a) {
         if (a[i] != kP[i]) return a[i] > kP[i];
     return true;
 }
-inline Fq add(const Fq& a, const Fq& b) {
-    Fq r;
-    u128 c = 0;
-    for (int i = 0; i < 4; i++) {
-        c += (u128)a.v[i] + b.v[i];
-        r.v[i] = (uint64_t)c;
-        c >>= 64;
-    }
-    if (geq_p(r.v)) {      // a + b < 2p < 2^255: no carry out
-        u128 bw = 0;
-        for (int i = 0; i < 4; i++) {
-            u128 d = (u128)r.v[i] - kP[i] - (uint64_t)bw;
-            r.v[i] = (uint64_t)d;
-            bw = (d >> 64) & 1;
-        }
-    }
-    return r;
+// r = t - p if t >= p else t   (t < 2p), branch-free adc / sbb chains
+inline Fq cond_sub_p(uint64_t t0, uint64_t t1, uint64_t t2, uint64_t t3) {
+    unsigned long long s0, s1, s2, s3;
+    unsigned char bw = _subborrow_u64(0, t0, kP[0], &s0);
+    bw = _subborrow_u64(bw, t1, kP[1], &s1);
+    bw = _subborrow_u64(bw, t2, kP[2], &s2);
+    bw = _subborrow_u64(bw, t3, kP[3], &s3);
+    const uint64_t keep = 0 - (uint64_t)bw;      // all ones if t < p
+    return {{(t0 & keep) | (s0 & ~keep), (t1 & keep) | (s1 & ~keep), (t2 & keep) | (s2 & ~keep), (t3 & keep) | (s3 & ~keep)}};
+}
+inline Fq add(const Fq& a, const Fq& b) {      // a + b < 2p < 2^255: no carry out of the top word
+    unsigned long long t0, t1, t2, t3;
+    unsigned char c = _addcarry_u64(0, a.v[0], b.v[0], &t0);
+    c = _addcarry_u64(c, a.v[1], b.v[1], &t1);
+    c = _addcarry_u64(c, a.v[2], b.v[2], &t2);
+    _addcarry_u64(c, a.v[3], b.v[3], &t3);
+    return cond_sub_p(t0, t1, t2, t3);
 }
 inline Fq sub(const Fq& a, const Fq& b) {
-    Fq r;
-    u128 bw = 0;
-    for (int i = 0; i < 4; i++) {
-        u128 d = (u128)a.v[i] - b.v[i] - (uint64_t)bw;
-        r.v[i] = (uint64_t)d;
-        bw = (d >> 64) & 1;
-    }
-    if (bw) {
-        u128 c = 0;
-        for (int i = 0; i < 4; i++) {
-            c += (u128)r.v[i] + kP[i];
-            r.v[i] = (uint64_t)c;
-            c >>= 64;
-        }
-    }
-    return r;
+    unsigned long long t0, t1, t2, t3;
+    unsigned char bw = _subborrow_u64(0, a.v[0], b.v[0], &t0);
+    bw = _subborrow_u64(bw, a.v[1], b.v[1], &t1);
+    bw = _subborrow_u64(bw, a.v[2], b.v[2], &t2);
+    bw = _subborrow_u64(bw, a.v[3], b.v[3], &t3);
+    const uint64_t m = 0 - (uint64_t)bw;          // all ones if a < b: add p back
+    unsigned long long r0, r1, r2, r3;
+    unsigned char c = _addcarry_u64(0, t0, kP[0] & m, &r0);
+    c = _addcarry_u64(c, t1, kP[1] & m, &r1);
+    c = _addcarry_u64(c, t2, kP[2] & m, &r2);
+    _addcarry_u64(c, t3, kP[3] & m, &r3);
+    return {{r0, r1, r2, r3}};
 }
 inline Fq neg(const Fq& a) { return is_zero(a) ? a : sub(kZero, a); }
 inline Fq dbl(const Fq& a) { return add(a, a); }
+// CIOS with the reduction row fused into the product row; q < 2^254 leaves the top word headroom, so the
+// running value fits 4 words + the two carries added at the end of each row
 inline Fq mul(const Fq& a, const Fq& b) {
-    uint64_t t[6] = {0, 0, 0, 0, 0, 0};
+    uint64_t t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+#pragma GCC unroll 4
     for (int i = 0; i < 4; i++) {
-        u128 c = 0;
-        for (int j = 0; j < 4; j++) {
-            c += (u128)a.v[j] * b.v[i] + t[j];
-            t[j] = (uint64_t)c;
-            c >>= 64;
-        }
-        c += t[4];
-        t[4] = (uint64_t)c;
-        t[5] = (uint64_t)(c >> 64);
-        const uint64_t k = t[0] * kInv;
-        c = (u128)k * kP[0] + t[0];
-        c >>= 64;
-        for (int j = 1; j < 4; j++) {
-            c += (u128)k * kP[j] + t[j];
-            t[j - 1] = (uint64_t)c;
-            c >>= 64;
-        }
-        c += t[4];
-        t[3] = (uint64_t)c;
-        t[4] = t[5] + (uint64_t)(c >> 64);
+        u128 c = (u128)a.v[0] * b.v[i] + t0;
+        const uint64_t lo = (uint64_t)c;
+        uint64_t ca = (uint64_t)(c >> 64);
+        const uint64_t m = lo * kInv;
+        u128 d = (u128)m * kP[0] + lo;
+        uint64_t cm = (uint64_t)(d >> 64);
+        c = (u128)a.v[1] * b.v[i] + t1 + ca;
+        ca = (uint64_t)(c >> 64);
+        d = (u128)m * kP[1] + (uint64_t)c + cm;
+        t0 = (uint64_t)d;
+        cm = (uint64_t)(d >> 64);
+        c = (u128)a.v[2] * b.v[i] + t2 + ca;
+        ca = (uint64_t)(c >> 64);
+        d = (u128)m * kP[2] + (uint64_t)c + cm;
+        t1 = (uint64_t)d;
+        cm = (uint64_t)(d >> 64);
+        c = (u128)a.v[3] * b.v[i] + t3 + ca;
+        ca = (uint64_t)(c >> 64);
+        d = (u128)m * kP[3] + (uint64_t)c + cm;
+        t2 = (uint64_t)d;
+        cm = (uint64_t)(d >> 64);
+        t3 = cm + ca;
     }
-    Fq r = {{t[0], t[1], t[2], t[3]}};
-    if (t[4] || geq_p(r.v)) {
-        u128 bw = 0;
-        for (int i = 0; i < 4; i++) {
-            u128 d = (u128)r.v[i] - kP[i] - (uint64_t)bw;
-            r.v[i] = (uint64_t)d;
-            bw = (d >> 64) & 1;
-        }
-    }
-    return r;
+    return cond_sub_p(t0, t1, t2, t3);      // result < 2p
 }
 inline Fq sqr(const Fq& a) { return mul(a, a); }
 inline Fq inv(const Fq& a) {    // a^(p-2)
@@ -242,11 +236,32 @@ inline bool f12_is_one(const Fq12& a) {
         if (!is_zero(a.c[i])) return false;
     return true;
 }
+// (a0 + a1 x + a2 x^2)(b0 + b1 x + b2 x^2) -> c[0..4], 6 Fq2 multiplications (Karatsuba)
+inline void poly3_mul(const Fq2* a, const Fq2* b, Fq2* c) {
+    Fq2 v0 = mul(a[0], b[0]), v1 = mul(a[1], b[1]), v2 = mul(a[2], b[2]);
+    c[0] = v0;
+    c[1] = sub(sub(mul(add(a[0], a[1]), add(b[0], b[1])), v0), v1);
+    c[2] = add(sub(sub(mul(add(a[0], a[2]), add(b[0], b[2])), v0), v2), v1);
+    c[3] = sub(sub(mul(add(a[1], a[2]), add(b[1], b[2])), v1), v2);
+    c[4] = v2;
+}
+// a = P0 + P1 w^3, b = Q0 + Q1 w^3 (halves of degree < 3 in w): Karatsuba over the halves, 18 Fq2 multiplications
 Fq12 f12_mul(const Fq12& a, const Fq12& b) {
+    Fq2 lo[5], hi[5], mid[5], sa[3], sb[3];
+    poly3_mul(a.c, b.c, lo);
+    poly3_mul(a.c + 3, b.c + 3, hi);
+    for (int i = 0; i < 3; i++) {
+        sa[i] = add(a.c[i], a.c[i + 3]);
+        sb[i] = add(b.c[i], b.c[i + 3]);
+    }
+    poly3_mul(sa, sb, mid);
     Fq2 t[11];
     for (int i = 0; i < 11; i++) t[i] = kZero2;
-    for (int i = 0; i < 6; i++)
-        for (int j = 0; j < 6; j++) t[i + j] = add(t[i + j], mul(a.c[i], b.c[j]));
+    for (int i = 0; i < 5; i++) {
+        t[i] = add(t[i], lo[i]);
+        t[i + 3] = add(t[i + 3], sub(sub(mid[i], lo[i]), hi[i]));
+        t[i + 6] = add(t[i + 6], hi[i]);
+    }
     Fq12 r;
     for (int k = 0; k < 6; k++) r.c[k] = k < 5 ? add(t[k], mul_xi(t[k + 6])) : t[k];
     return r;

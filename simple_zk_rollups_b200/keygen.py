@@ -3,7 +3,7 @@
 Stands where the reference runs `snarkjs setup --protocol groth` (prover/package.json:34,37); the
 toxic waste is an explicit input, so these are TEST / BENCHMARK keys.  Output is the websnark
 binary proving key -- byte-identical to binarifyProvingKey(snarkjs pk JSON) for the same
-(R1CS, toxic waste) -- plus the verifying key as Python ints.
+(R1CS, toxic waste) -- plus the verifying key as Python ints (and as the binary block zkr_vkey_load_bin takes, vk["bin"]).
 """
 import ctypes as C
 import struct
@@ -91,5 +91,6 @@ def synth_setup(ctx, r1cs, toxic):
     assert pk_bin.size == off
     vk = dict(protocol="groth", nPublic=l, vk_alfa_1=_g1(vkb[0:64]), vk_beta_2=_g2(vkb[192:320]),
               vk_gamma_2=_g2(vkb[320:448]), vk_delta_2=_g2(vkb[448:576]),
-              IC=[_g1(vkb[576 + 64 * i:640 + 64 * i]) for i in range(l + 1)])
+              IC=[_g1(vkb[576 + 64 * i:640 + 64 * i]) for i in range(l + 1)],
+              bin=vkb)                 # the block zkr_vkey_load_bin takes
     return pk_bin, vk

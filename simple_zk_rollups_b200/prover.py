@@ -17,7 +17,7 @@ import numpy as np
 
 from . import _lib
 from .binarify import R as SNARK_FIELD_SIZE
-from .binarify import binarifyProvingKey, binarifyWitness, proof_from_bytes
+from .binarify import binarifyProvingKey, binarifyWitness, proof_from_bytes, proof_to_bytes
 
 
 class Groth16Prover:
@@ -29,11 +29,15 @@ class Groth16Prover:
         _lib.check(self.L.zkr_ctx_create(device, C.byref(self.ctx)))
         self.device = device
         self._keys = []
+        self._vkeys = []
 
     def close(self):
         for k in self._keys:
             self.L.zkr_pkey_free(k)
         self._keys = []
+        for k in self._vkeys:
+            self.L.zkr_vkey_free(k)
+        self._vkeys = []
         if self.ctx:
             self.L.zkr_ctx_destroy(self.ctx)
             self.ctx = C.c_void_p()
@@ -53,6 +57,34 @@ class Groth16Prover:
         _lib.check(self.L.zkr_pkey_load_json(self.ctx, data, len(data), C.byref(h)))
         self._keys.append(h)
         return h
+
+    def load_vkey(self, verifyingKey):
+        """verifyingKey: snarkjs verification_key.json as dict / JSON text, or the binary vk block of
+        keygen.synth_setup (vk["bin"]).  IC tables become resident on this GPU (zkr_vkey_load_*)."""
+        import json
+        h = C.c_void_p()
+        if isinstance(verifyingKey, dict):
+            verifyingKey = json.dumps(verifyingKey)
+        if isinstance(verifyingKey, str):
+            data = verifyingKey.encode()
+            _lib.check(self.L.zkr_vkey_load_json(self.ctx, data, len(data), C.byref(h)))
+        else:
+            arr = np.frombuffer(verifyingKey, dtype=np.uint8) if isinstance(verifyingKey, (bytes, bytearray)) else verifyingKey
+            _lib.check(self.L.zkr_vkey_load_bin(self.ctx, _lib.buf_ptr(arr), arr.size, C.byref(h)))
+        self._vkeys.append(h)
+        return h
+
+    def verify(self, vkey, proof, publicSignals):
+        """groth.isValid(vk, proof, publicSignals) (common.ts:30-34) as the on-chain predicate
+        (TxVerifier.sol:258-276).  proof: 256-byte buffer or the {pi_a, pi_b, pi_c} object."""
+        if isinstance(proof, dict):
+            proof = proof_to_bytes(proof)
+        pb = np.frombuffer(bytes(proof), dtype=np.uint8)
+        pub = np.frombuffer(b"".join(int(x).to_bytes(32, "little") for x in publicSignals), dtype=np.uint8)
+        ok = C.c_int()
+        _lib.check(self.L.zkr_verify(self.ctx, vkey, _lib.buf_ptr(pb), _lib.buf_ptr(pub) if pub.size else None,
+                                     len(publicSignals), C.byref(ok)))
+        return bool(ok.value)
 
     def load_key_sharded(self, pk_bin, rank, world):
         """Keep only `rank`'s point range of the five base sets (one proof split over `world` GPUs)."""
@@ -136,10 +168,17 @@ def createProofGenerator(provingKey, verifyingKey, circuitName, calculateWitness
         stands for circom compile + snarkjs Circuit.calculateWitness (common.ts:12-21), which stay
         on the host in the reference as well.
     isValid(verifyingKey, proof, publicSignals) -> bool stands for snarkjs groth.isValid
-        (common.ts:30-34); when given, an invalid proof raises "Invalid proof generated" (common.ts:36-38).
+        (common.ts:30-34); an invalid proof raises "Invalid proof generated" (common.ts:36-38).  Default:
+        the library's own verifier (zkr_verify, the TxVerifier.sol:258-276 predicate) on verifyingKey;
+        pass verifyingKey=None to skip the self-check.
     The returned callable is synchronous; the reference's is async only because websnark is."""
     p = prover or default_prover()
     key = p.load_key(binarifyProvingKey(provingKey) if isinstance(provingKey, dict) else provingKey)
+    if isValid is None and verifyingKey is not None:
+        vkey = p.load_vkey(verifyingKey)             # once per circuit; IC tables resident on the GPU
+
+        def isValid(_vk, proof, publicSignals):      # noqa: F811  (zkr_verify: GPU vk_x + host pairing product)
+            return p.verify(vkey, proof, publicSignals)
 
     def generate(circuitInputs, r=None, s=None):
         witness, n_pub = calculateWitness(circuitName, circuitInputs)
