@@ -1,6 +1,9 @@
 // libzkr context / error plumbing (C-ABI: zkr_ctx_*, zkr_strerror, zkr_last_error, zkr_version).
 // zkr_ctx_create stands where the reference calls buildBn128()
 // (/root/reference/operator/src/snarks/common.ts:23) -- but it is created once, not per proof.
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
 
 namespace zkr {
@@ -75,7 +78,18 @@ extern "C" int zkr_ctx_create(int device, zkr_ctx** out) {
     for (int i = 0; i < kNumStreams; i++) {
         // equal priorities on purpose: giving the H chain a high-priority stream made the overlapped proof
         // slower (19.3 ms vs 17.8 ms at 2^20) -- the MSMs it displaces are the long pole
-        ZKR_CUDA(cudaStreamCreateWithFlags(&c->s[i], cudaStreamNonBlocking));
+        // ZKR_STREAM_PRIO="p0,p1,..." (experiment knob, tools/prio_sweep.py): CUDA priority per internal stream
+        // (0 = default, negative = higher); s[0] = H chain, s[1] = A, s[2] = B1, s[3] = B2, s[4] = C
+        int prio = 0;
+        if (const char* e = getenv("ZKR_STREAM_PRIO")) {
+            const char* q = e;
+            for (int k = 0; k < i && q; k++) {
+                q = strchr(q, ',');
+                if (q) q++;
+            }
+            if (q) prio = atoi(q);
+        }
+        ZKR_CUDA(cudaStreamCreateWithPriority(&c->s[i], cudaStreamNonBlocking, prio));
         ZKR_CUDA(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
     }
     ZKR_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));

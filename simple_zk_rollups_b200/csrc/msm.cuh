@@ -19,6 +19,8 @@
 //   * reduction sum_b (b+1) B_b: per-thread running sums over K consecutive buckets, then a block
 //     suffix-scan turns sum_l l*S_l into plain sums; one more single-block kernel finishes.
 #pragma once
+#include <cstdlib>
+
 #include <cub/device/device_radix_sort.cuh>
 
 #include "common.cuh"
@@ -27,7 +29,14 @@
 namespace zkr {
 
 constexpr int kAccumThreads = 128;
-constexpr int kLevelLog = 4;          // boundary levels: 16 entries per thread
+constexpr int kLevelLog = 4;          // boundary levels: 16 entries per thread ...
+constexpr int kLevelLogBig = 2;       // ... except while the list is long: 4 per thread keeps ~4x more warps in flight
+constexpr size_t kLevelBigMin = 1u << 16;
+inline int level_log(size_t cnt) {
+    const int forced = getenv("ZKR_LEVEL_LOG_BIG") ? atoi(getenv("ZKR_LEVEL_LOG_BIG")) : 0;   // experiment knob
+    const int big = forced >= 1 && forced <= kLevelLog ? forced : kLevelLogBig;
+    return cnt >= kLevelBigMin ? big : kLevelLog;
+}
 constexpr uint32_t kNegBit = 0x80000000u;
 
 struct MsmPlan {
@@ -532,7 +541,7 @@ int bases_build(zkr_ctx* ctx, zkr_bases* b, const char* h_points, size_t n_src, 
     ZKR_CUDA(cudaMalloc(&wk.cub_tmp, wk.cub_bytes ? wk.cub_bytes : 1));
     ZKR_CUDA(cudaMalloc(&wk.buckets, XB * (size_t)b->plan.nbuckets));
     const size_t bnd0 = 2 * (size_t)b->T1p;
-    const size_t lvl = (size_t)1 << kLevelLog;
+    const size_t lvl = 2;                 // smallest per-thread count any boundary level may use (level_log >= 1)
     size_t bnd1 = 2 * (((bnd0 + lvl - 1) / lvl + 63) / 64 * 64);
     if (bnd1 < 2 * (size_t)kFinishThreads) bnd1 = 2 * (size_t)kFinishThreads;
     ZKR_CUDA(cudaMalloc(&wk.bnd[0], XB * bnd0));
@@ -594,8 +603,9 @@ int msm_run(zkr_ctx* ctx, cudaStream_t st, const zkr_bases* b, const uint32_t* d
     // boundary levels
     size_t cnt = 2 * (size_t)b->T1p;
     int cur = 0;
-    const size_t lvl = (size_t)1 << kLevelLog;
     for (;;) {
+        const int llog = level_log(cnt);
+        const size_t lvl = (size_t)1 << llog;
         if (cnt <= kFinishMax) {
             ZKR_LAUNCH(ctx, k_accum_finish<F>, 1, kFinishThreads, 0, st, wk.bnd_keys[cur], (XYZZ<F>*)wk.bnd[cur],
                        wk.bnd_keys[cur ^ 1], (XYZZ<F>*)wk.bnd[cur ^ 1], (uint32_t)cnt, buckets, nb);
@@ -605,7 +615,7 @@ int msm_run(zkr_ctx* ctx, cudaStream_t st, const zkr_bases* b, const uint32_t* d
         const size_t T = (cnt + lvl - 1) / lvl;
         const unsigned blocks = (unsigned)((T + 63) / 64);
         ZKR_LAUNCH(ctx, k_accum_xyzz<F>, blocks, 64, 0, st, wk.bnd_keys[cur], (const XYZZ<F>*)wk.bnd[cur],
-                   (uint32_t)cnt, kLevelLog, buckets, (XYZZ<F>*)wk.bnd[cur ^ 1], wk.bnd_keys[cur ^ 1], nb, fin);
+                   (uint32_t)cnt, llog, buckets, (XYZZ<F>*)wk.bnd[cur ^ 1], wk.bnd_keys[cur ^ 1], nb, fin);
         if (fin) break;
         cnt = 2 * T;          // threads past T only pad their block; their slots are never read
         cur ^= 1;

@@ -12,6 +12,7 @@
 //   pi_c = sum_{i>l} w_i C_i - rs delta1  (one MSM)  +  sum h_j hExps_j (one MSM)  +  s pi_a + r pib1
 // The blinding terms ride inside the MSMs as extra bases, so the only scalar multiplications left
 // are s*pi_a and r*pib1 (two threads, overlapped with the G2 / C / H MSMs on other streams).
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 
@@ -403,17 +404,29 @@ static int prove_enqueue(zkr_ctx* ctx, const zkr_pkey* pk, char* d_proof, bool t
     cudaStream_t sH = par ? ctx->s[0] : us, sA = par ? ctx->s[1] : us, sB1 = par ? ctx->s[2] : us,
                  sB2 = par ? ctx->s[3] : us, sC = par ? ctx->s[4] : us;
     const uint32_t* w = (const uint32_t*)pk->wext;
+    // experiment knob (tools/prio_sweep.py): ZKR_H_FIRST=1 runs sparse LC + the NTT pipeline before any MSM starts
+    const bool h_first = getenv("ZKR_H_FIRST") && atoi(getenv("ZKR_H_FIRST")) != 0;
+    auto h_front = [&]() -> int {
+        if (timed) cudaEventRecord(ev[0], sH);
+        ZKR_LAUNCH(ctx, k_sparse_lc, dim3(ceil_div(m, 128), 2), 128, 0, sH, pk->a_ptr, pk->a_sig, pk->a_coef, pk->b_ptr,
+                   pk->b_sig, pk->b_coef, pk->wext, pk->at, pk->bt, m);
+        if (timed) cudaEventRecord(ev[1], sH);
+        ZKR_TRY(h_pipeline(ctx, sH, pk->at, pk->bt, pk->st, pk->h, pk->log_m, true));
+        if (timed) cudaEventRecord(ev[2], sH);
+        return ZKR_OK;
+    };
+    if (h_first && par) {
+        ZKR_TRY(h_front());
+        ZKR_CUDA(cudaEventRecord(ctx->ev_join[0], sH));
+        cudaStream_t others[4] = {sA, sB1, sB2, sC};
+        for (cudaStream_t o : others) ZKR_CUDA(cudaStreamWaitEvent(o, ctx->ev_join[0], 0));
+    }
     // heaviest first: the G2 MSM costs ~3 G1 MSMs
     if (timed) cudaEventRecord(ev[6], sB2);
     ZKR_TRY(msm_run_g2(ctx, sB2, pk->B2, w, pk->res + R_B2));
     if (timed) cudaEventRecord(ev[7], sB2);
     // H chain
-    if (timed) cudaEventRecord(ev[0], sH);
-    ZKR_LAUNCH(ctx, k_sparse_lc, dim3(ceil_div(m, 128), 2), 128, 0, sH, pk->a_ptr, pk->a_sig, pk->a_coef, pk->b_ptr,
-               pk->b_sig, pk->b_coef, pk->wext, pk->at, pk->bt, m);
-    if (timed) cudaEventRecord(ev[1], sH);
-    ZKR_TRY(h_pipeline(ctx, sH, pk->at, pk->bt, pk->st, pk->h, pk->log_m, true));
-    if (timed) cudaEventRecord(ev[2], sH);
+    if (!(h_first && par)) ZKR_TRY(h_front());
     ZKR_TRY(msm_run_g1(ctx, sH, pk->H, (const uint32_t*)(pk->h + pk->h_lo), pk->res + R_H));
     if (timed) cudaEventRecord(ev[3], sH);
     // A, then s * pi_a

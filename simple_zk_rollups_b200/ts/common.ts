@@ -1,7 +1,7 @@
 // Drop-in replacement for operator/src/snarks/common.ts of kendricktan/simple-zk-rollups.
-// SOURCE ONLY here (no node in the build image).  Same exports, same return shape; the three lines that
-// change are marked.  Witness generation, the isValid self-check and the Solidity formatting are the
-// reference's own code, untouched.
+// SOURCE ONLY here (no node in the build image).  Same exports, same return shape; the lines that
+// change are marked.  Witness generation and the Solidity formatting are the
+// reference's own code, untouched; the isValid self-check keeps its place and its exception but calls zkr.verify.
 import * as path from "path";
 import * as compiler from "circom";
 import * as crypto from "crypto";
@@ -35,6 +35,8 @@ const randomScalar = (): Uint8Array => {
 export const createProofGenerator = (provingKey, verifyingKey, circuitName) => {
   // CHANGED: the key is binarified and uploaded ONCE (the reference re-encodes it on every proof, common.ts:28)
   const key = zkr.loadKey(binarifyProvingKey(provingKey));
+  // CHANGED: the verifying key's IC tables are uploaded once; the self-check below runs in libzkr (zkr_verify)
+  const vkey = zkr.loadVerifyingKey(Buffer.from(JSON.stringify(stringifyBigInts(verifyingKey))));
 
   return async circuitInputs => {
     const circuitDef = await compiler(
@@ -59,11 +61,9 @@ export const createProofGenerator = (provingKey, verifyingKey, circuitName) => {
       protocol: "groth"
     };
 
-    const isValid = groth.isValid(
-      unstringifyBigInts(verifyingKey),
-      unstringifyBigInts(proof),
-      unstringifyBigInts(publicSignals)
-    );
+    // CHANGED (was: groth.isValid(vk, proof, publicSignals) on the JS BigInt path, seconds per call):
+    // same acceptance predicate as contracts/contracts/TxVerifier.sol:258-276
+    const isValid = zkr.verify(vkey, p, binarifyWitness(publicSignals));
 
     if (!isValid) {
       throw new Error("Invalid proof generated");

@@ -7,9 +7,13 @@
 //
 // Exposes to JS:
 //   loadKey(pkBin: ArrayBuffer) -> keyHandle (external)            zkr_pkey_load_bin, once per circuit
+//   loadKeyJson(pkJsonText: Buffer) -> keyHandle                   zkr_pkey_load_json: proving_key.json text, native parse
 //   prove(key, witnessBin: ArrayBuffer, r?: Uint8Array(32), s?: Uint8Array(32)) -> Promise<Uint8Array(256)>
 //        zkr_prove on a worker thread (napi_create_async_work), so the Express event loop never blocks
 //        (the reference's websnark call is async for the same reason, operator/src/snarks/common.ts:29)
+//   loadVerifyingKey(vkJsonText: Buffer) -> vkHandle               zkr_vkey_load_json, once per circuit
+//   verify(vk, proof: Uint8Array(256), publicSignalsBin: ArrayBuffer) -> boolean
+//        zkr_verify: replaces groth.isValid (common.ts:30-34); ~ms, synchronous
 #include <node_api.h>
 
 #include <cstring>
@@ -54,6 +58,75 @@ napi_value LoadKey(napi_env env, napi_callback_info info) {
     napi_value ext;
     napi_create_external(env, pk, free_key, nullptr, &ext);
     return ext;
+}
+
+napi_value LoadKeyJson(napi_env env, napi_callback_info info) {
+    size_t argc = 1;
+    napi_value argv[1];
+    napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr);
+    void* buf;
+    size_t len;
+    if (argc < 1 || napi_get_buffer_info(env, argv[0], &buf, &len) != napi_ok) {
+        napi_throw_type_error(env, nullptr, "loadKeyJson(pkJsonText: Buffer)");
+        return nullptr;
+    }
+    if (!ensure_ctx(env)) return nullptr;
+    zkr_pkey* pk = nullptr;
+    if (zkr_pkey_load_json(g_ctx, static_cast<const char*>(buf), len, &pk) != ZKR_OK) {
+        napi_throw_error(env, "ZKR_BADKEY", zkr_last_error());
+        return nullptr;
+    }
+    napi_value ext;
+    napi_create_external(env, pk, free_key, nullptr, &ext);
+    return ext;
+}
+
+void free_vkey(napi_env, void* data, void*) { zkr_vkey_free(static_cast<zkr_vkey*>(data)); }
+
+napi_value LoadVerifyingKey(napi_env env, napi_callback_info info) {
+    size_t argc = 1;
+    napi_value argv[1];
+    napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr);
+    void* buf;
+    size_t len;
+    if (argc < 1 || napi_get_buffer_info(env, argv[0], &buf, &len) != napi_ok) {
+        napi_throw_type_error(env, nullptr, "loadVerifyingKey(vkJsonText: Buffer)");
+        return nullptr;
+    }
+    if (!ensure_ctx(env)) return nullptr;
+    zkr_vkey* vk = nullptr;
+    if (zkr_vkey_load_json(g_ctx, static_cast<const char*>(buf), len, &vk) != ZKR_OK) {
+        napi_throw_error(env, "ZKR_BADKEY", zkr_last_error());
+        return nullptr;
+    }
+    napi_value ext;
+    napi_create_external(env, vk, free_vkey, nullptr, &ext);
+    return ext;
+}
+
+// verify(vk, proof: Uint8Array(256), publicSignalsBin: ArrayBuffer of n x 32 B LE) -> boolean
+napi_value Verify(napi_env env, napi_callback_info info) {
+    size_t argc = 3;
+    napi_value argv[3];
+    napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr);
+    void *vkv, *pdata, *sbuf;
+    size_t plen, slen, off;
+    napi_typedarray_type ty;
+    napi_value ab;
+    if (argc < 3 || napi_get_value_external(env, argv[0], &vkv) != napi_ok ||
+        napi_get_typedarray_info(env, argv[1], &ty, &plen, &pdata, &ab, &off) != napi_ok || plen != ZKR_PROOF_BYTES ||
+        napi_get_arraybuffer_info(env, argv[2], &sbuf, &slen) != napi_ok || slen % 32) {
+        napi_throw_type_error(env, nullptr, "verify(vk, proof: Uint8Array(256), publicSignalsBin: ArrayBuffer)");
+        return nullptr;
+    }
+    int valid = 0;
+    if (zkr_verify(g_ctx, static_cast<zkr_vkey*>(vkv), pdata, sbuf, slen / 32, &valid) != ZKR_OK) {
+        napi_throw_error(env, "ZKR_VERIFY", zkr_last_error());      // the contract's reverts (TxVerifier.sol:261,265)
+        return nullptr;
+    }
+    napi_value out;
+    napi_get_boolean(env, valid != 0, &out);
+    return out;
 }
 
 struct ProveJob {
@@ -137,6 +210,12 @@ napi_value Init(napi_env env, napi_value exports) {
     napi_set_named_property(env, exports, "loadKey", f);
     napi_create_function(env, "prove", NAPI_AUTO_LENGTH, Prove, nullptr, &f);
     napi_set_named_property(env, exports, "prove", f);
+    napi_create_function(env, "loadKeyJson", NAPI_AUTO_LENGTH, LoadKeyJson, nullptr, &f);
+    napi_set_named_property(env, exports, "loadKeyJson", f);
+    napi_create_function(env, "loadVerifyingKey", NAPI_AUTO_LENGTH, LoadVerifyingKey, nullptr, &f);
+    napi_set_named_property(env, exports, "loadVerifyingKey", f);
+    napi_create_function(env, "verify", NAPI_AUTO_LENGTH, Verify, nullptr, &f);
+    napi_set_named_property(env, exports, "verify", f);
     return exports;
 }
 
