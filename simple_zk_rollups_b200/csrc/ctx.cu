@@ -76,11 +76,13 @@ extern "C" int zkr_ctx_create(int device, zkr_ctx** out) {
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     for (int i = 0; i < kNumStreams; i++) {
-        // equal priorities on purpose: giving the H chain a high-priority stream made the overlapped proof
-        // slower (19.3 ms vs 17.8 ms at 2^20) -- the MSMs it displaces are the long pole
-        // ZKR_STREAM_PRIO="p0,p1,..." (experiment knob, tools/prio_sweep.py): CUDA priority per internal stream
-        // (0 = default, negative = higher); s[0] = H chain, s[1] = A, s[2] = B1, s[3] = B2, s[4] = C
-        int prio = 0;
+        // Stream priorities (measured with tools/prio_sweep.py at 2^20, profiles/r01_sched_sweep.json): the G2 MSM is
+        // the longest chain and the H chain the most serial one; B2 highest + H high gives 16.91 ms against 17.17 ms
+        // with equal priorities, H alone high 17.96 ms (it displaces the long pole), NTT-before-MSMs 18.5 ms.
+        // s[0] = H chain, s[1] = A, s[2] = B1, s[3] = B2, s[4] = C.  ZKR_STREAM_PRIO="p0,p1,..." overrides (0 =
+        // default, negative = higher).
+        static const int kDefaultPrio[kNumStreams] = {-1, 0, 0, -2, 0, 0};
+        int prio = kDefaultPrio[i];
         if (const char* e = getenv("ZKR_STREAM_PRIO")) {
             const char* q = e;
             for (int k = 0; k < i && q; k++) {

@@ -34,7 +34,7 @@ constexpr int kLevelLogBig = 2;       // ... except while the list is long: 4 pe
 constexpr size_t kLevelBigMin = 1u << 16;
 inline int level_log(size_t cnt) {
     const int forced = getenv("ZKR_LEVEL_LOG_BIG") ? atoi(getenv("ZKR_LEVEL_LOG_BIG")) : 0;   // experiment knob
-    const int big = forced >= 1 && forced <= kLevelLog ? forced : kLevelLogBig;
+    const int big = forced >= 2 && forced <= kLevelLog ? forced : kLevelLogBig;   // 1 would never shrink the list (2 in, 2 out)
     return cnt >= kLevelBigMin ? big : kLevelLog;
 }
 constexpr uint32_t kNegBit = 0x80000000u;

@@ -18,7 +18,7 @@ TOXIC = (0x1234567890ABCDEF1234567890ABCDEF1234567, 0x22222222222222222222222222
          0x555555555555555555555555555555555555555551)
 CONFIGS = {"equal": "0,0,0,0,0,0", "b2_high": "0,0,0,-1,0,0", "h_high": "-1,0,0,0,0,0", "b2_h_high": "-1,0,0,-1,0,0",
            "b2_highest_h_high": "-1,0,0,-2,0,0", "h_first": "0,0,0,0,0,0;H", "h_first_b2_high": "0,0,0,-1,0,0;H",
-           "equal_lvl4": "0,0,0,0,0,0;L4", "equal_lvl3": "0,0,0,0,0,0;L3", "equal_lvl1": "0,0,0,0,0,0;L1"}
+           "equal_lvl4": "0,0,0,0,0,0;L4", "equal_lvl3": "0,0,0,0,0,0;L3"}
 
 
 def main():
