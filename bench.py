@@ -244,6 +244,16 @@ def run_ours(args):
                             "peak_source": hbm_src, "launches": nt_cnt, "avg_launch_ms": round(nt_ms / nt_cnt, 4),
                             "note": "64 B per element per pass (read once + write once); the pass is IMAD-bound "
                                     "(~6 modmul per 64 B), see DESIGN.md"}
+            # the binding roof: butterfly modmuls, (m/2) log2 m per transform, 6 transforms per proof
+            log_m = m.bit_length() - 1
+            bfly = 6.0 * prof_steps * (m // 2) * log_m
+            roofline_ntt["imad"] = {
+                "bound": "imad", "butterfly_modmuls_per_proof": int(bfly / prof_steps),
+                "achieved_timad_per_s": round(bfly * MODMUL_IMAD / (nt_ms * 1e-3) / 1e12, 3),
+                "frac_of_plain_imad_peak": round(bfly * MODMUL_IMAD / (nt_ms * 1e-3) / imad_peak.value, 4),
+                "frac_of_practical_modmul_peak": round(bfly / (nt_ms * 1e-3) / modmul_peak.value, 4),
+                "note": "algorithmic butterflies only; inter-pass / coset twiddle products (~1 extra modmul per element "
+                        "per pass) are not counted"}
         # ---- CPU baseline: the C restatement of the reference algorithm on this box's host cores
         cpu = None if args.no_cpu else cpu_baseline(pk_bin, wbytes, rs, out.tobytes(), args)
         value = world * args.steps / (ms * 1e-3)

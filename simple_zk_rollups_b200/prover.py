@@ -127,6 +127,31 @@ class Groth16Prover:
         return int(self.L.zkr_ctx_kernel_launches(self.ctx))
 
 
+def prove_batch(provers, keys, witness_bins, rs=None):
+    """zkr_prove_batch: n independent proofs over len(provers) contexts (one per GPU; keys[i] is the same circuit's
+    key loaded on provers[i]), round-robin, one proof in flight per GPU -- the shape of many genTxVerifierProof calls
+    (operator/src/snarks/tx.ts:6-10) drained by an operator batch loop.  witness_bins: list of binarifyWitness
+    outputs; rs: optional list of (r, s) ints (default 0, 0).  -> list of 256-byte proofs, in input order."""
+    L = provers[0].L
+    n = len(witness_bins)
+    if n == 0:
+        return []
+    ws = [np.frombuffer(w, dtype=np.uint8) if isinstance(w, (bytes, bytearray)) else w for w in witness_bins]
+    n_signals = ws[0].size // 32
+    if any(w.size != ws[0].size for w in ws):
+        raise ValueError("all witnesses of a batch must have the same length")
+    ctxs = (C.c_void_p * len(provers))(*[p.ctx for p in provers])
+    pks = (C.c_void_p * len(provers))(*keys)
+    wptrs = (C.c_void_p * n)(*[w.ctypes.data for w in ws])
+    rsb = None
+    if rs is not None:
+        rsb = np.frombuffer(b"".join(int(r).to_bytes(32, "little") + int(s).to_bytes(32, "little") for r, s in rs),
+                            dtype=np.uint8)
+    out = np.zeros(n * _lib.PROOF_BYTES, dtype=np.uint8)
+    _lib.check(L.zkr_prove_batch(ctxs, pks, len(provers), wptrs, n_signals, n, _lib.buf_ptr(rsb), _lib.buf_ptr(out)))
+    return [out[i * _lib.PROOF_BYTES:(i + 1) * _lib.PROOF_BYTES].tobytes() for i in range(n)]
+
+
 _default = None
 
 

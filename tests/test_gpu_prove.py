@@ -155,6 +155,38 @@ def test_prove_from_json_text(gp):
     assert ei.value.code == -2
 
 
+def test_prove_batch_round_robin(gp):
+    """zkr_prove_batch over two contexts (two GPUs when present, else two contexts on device 0): every proof of the
+    batch equals the oracle's for its own witness and (r, s), in input order; a bad witness fails the call."""
+    import torch
+    dev2 = 1 if torch.cuda.device_count() > 1 else 0
+    gp2 = prover.Groth16Prover(dev2)
+    try:
+        r1, w = synth.generate(150, 3, seed=31)
+        pk, vk, _ = g.setup(r1.to_dicts(), TOXIC)
+        pk_bin = bf.binarify_proving_key(pk)
+        keys = [gp.load_key(pk_bin), gp2.load_key(pk_bin)]
+        wits, rs = [], []
+        rng = random.Random(8)
+        for i in range(5):
+            wi = list(w)
+            if i % 2:                      # distinct (well-formed, circuit-violating) witnesses: websnark's H semantics
+                wi[7 + i] = (wi[7 + i] + 1000 + i) % R
+            wits.append(wi)
+            rs.append((rng.randrange(R), rng.randrange(R)))
+        proofs = prover.prove_batch([gp, gp2], keys, [bf.binarify_witness(x) for x in wits], rs)
+        assert len(proofs) == 5
+        for p, wi, (r, s) in zip(proofs, wits, rs):
+            assert p == g.proof_to_bytes(g.gen_proof(pk, wi, r, s, h_method=g.calc_h_websnark)[0])
+        assert prover.prove_batch([gp, gp2], keys, []) == []
+        bad = list(w)
+        bad[3] = R
+        with pytest.raises(_lib.ZkrError):
+            prover.prove_batch([gp, gp2], keys, [bf.binarify_witness(w), bf.binarify_witness(bad)])
+    finally:
+        gp2.close()
+
+
 @pytest.mark.parametrize("shape", ["withdraw", "tx", "tx_2p20"])
 def test_prove_full_size(gp, shape):
     """BASELINE configs[0..1] at full size: GPU setup -> prove -> toxic-waste exponent check (no MSM / NTT
