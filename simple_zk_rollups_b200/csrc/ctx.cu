@@ -76,12 +76,15 @@ extern "C" int zkr_ctx_create(int device, zkr_ctx** out) {
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     for (int i = 0; i < kNumStreams; i++) {
-        // Stream priorities (measured with tools/prio_sweep.py at 2^20, profiles/r01_sched_sweep.json): the G2 MSM is
-        // the longest chain and the H chain the most serial one; B2 highest + H high gives 16.91 ms against 17.17 ms
-        // with equal priorities, H alone high 17.96 ms (it displaces the long pole), NTT-before-MSMs 18.5 ms.
+        // Equal stream priorities on purpose.  tools/prio_sweep.py (profiles/r01_sched_sweep.json, 2^20, real blinding
+        // scalars): nine priority assignments over the five chains land within 17.12 .. 17.63 ms of the 17.22 ms of
+        // equal priorities (H + A + B1 high: 18.3 ms); two and three proofs in flight per GPU gain 3 % in proofs/s
+        // (profiles/r01_pipeline_check.json).  The GPU is saturated by the proof's bulk kernels; ordering them does
+        // not change the total.  (A first sweep with r = s = 0 favoured "B2 highest": with zero scalars the two
+        // blinding multiplications are free, which hides that they then end up on the critical path.)
         // s[0] = H chain, s[1] = A, s[2] = B1, s[3] = B2, s[4] = C.  ZKR_STREAM_PRIO="p0,p1,..." overrides (0 =
         // default, negative = higher).
-        static const int kDefaultPrio[kNumStreams] = {-1, 0, 0, -2, 0, 0};
+        static const int kDefaultPrio[kNumStreams] = {0, 0, 0, 0, 0, 0};
         int prio = kDefaultPrio[i];
         if (const char* e = getenv("ZKR_STREAM_PRIO")) {
             const char* q = e;

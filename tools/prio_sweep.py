@@ -16,9 +16,9 @@ from simple_zk_rollups_b200 import _lib, keygen, prover, synth  # noqa: E402
 TOXIC = (0x1234567890ABCDEF1234567890ABCDEF1234567, 0x2222222222222222222222222222222222221,
          0x3333333333333333333333333333333333333331, 0x44444444444444444444444444444444441,
          0x555555555555555555555555555555555555555551)
-CONFIGS = {"equal": "0,0,0,0,0,0", "b2_high": "0,0,0,-1,0,0", "h_high": "-1,0,0,0,0,0", "b2_h_high": "-1,0,0,-1,0,0",
-           "b2_highest_h_high": "-1,0,0,-2,0,0", "h_first": "0,0,0,0,0,0;H", "h_first_b2_high": "0,0,0,-1,0,0;H",
-           "equal_lvl4": "0,0,0,0,0,0;L4", "equal_lvl3": "0,0,0,0,0,0;L3"}
+CONFIGS = {"equal": "0,0,0,0,0,0", "b2_highest_h_high": "-1,0,0,-2,0,0", "ab_high": "0,-1,-1,0,0,0",
+           "ab_highest_b2_h_high": "-1,-2,-2,-1,0,0", "ab_b2_high": "0,-1,-1,-1,0,0", "b2_highest_ab_h_high": "-1,-1,-1,-2,0,0",
+           "ab_highest_h_high": "-1,-2,-2,0,0,0", "ab_highest_b2_high": "0,-2,-2,-1,0,0", "all_but_c_high": "-1,-1,-1,-1,0,0"}
 
 
 def main():
@@ -48,9 +48,12 @@ def main():
         w_dev = torch.from_numpy(wb.copy()).cuda()
         out = torch.zeros(256, dtype=torch.uint8, device="cuda")
         n = r1.nVars
+        rb = np.frombuffer((0x1F2E3D4C5B6A79881122334455667788 << 64 | 0x99AABBCCDDEEFF00).to_bytes(32, "little"), dtype=np.uint8)
+        sb = np.frombuffer((0x0123456789ABCDEF << 100 | 77).to_bytes(32, "little"), dtype=np.uint8)
 
         def run():
-            _lib.check(L.zkr_prove_dev(gp.ctx, key, C.c_void_p(w_dev.data_ptr()), n, None, None, C.c_void_p(out.data_ptr())))
+            _lib.check(L.zkr_prove_dev(gp.ctx, key, C.c_void_p(w_dev.data_ptr()), n, _lib.buf_ptr(rb), _lib.buf_ptr(sb),
+                                       C.c_void_p(out.data_ptr())))
         for _ in range(3):
             run()
         torch.cuda.synchronize()
