@@ -132,3 +132,19 @@ def test_null_arguments():
     assert L.zkr_pkey_json_to_bin(None, 0, C.byref(out), C.byref(n)) == -1
     assert L.zkr_witness_json_to_bin(b"[]", 2, None, C.byref(n)) == -1
     L.zkr_buf_free(None)
+
+
+def test_pkey_json_fabricated_rollup_shape_matches_host_mirror():
+    """A few thousand signals of random field values in the tx.circom key shape (73 public signals, polsC present,
+    1-3 non-zeros per column): the native converter equals the line-by-line Python mirror of binarify.ts."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from bench_keyjson import fabricate
+    j = fabricate(3000, 73, seed=5)
+    text = json.dumps(j)
+    got = binarify.binarifyProvingKeyJson(text)
+    assert got == binarify.binarifyProvingKey(json.loads(text))
+    n, l, m = j["nVars"], j["nPublic"], j["domainSize"]
+    assert int.from_bytes(got[0:4], "little") == n and int.from_bytes(got[4:8], "little") == l
+    assert int.from_bytes(got[36:40], "little") + 64 * m == len(got)          # pPointsHExps + hExps = end (binarify.ts:199-204)
