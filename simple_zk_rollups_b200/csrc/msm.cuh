@@ -52,6 +52,9 @@ struct MsmPlan {
             double cost = 10.0 * (double)n * W + 56.0 * (double)(1u << (c - 1));
             if (cost < best_cost) { best_cost = cost; best = c; }
         }
+        if (c_forced <= 0)
+            if (const char* e = getenv("ZKR_MSM_C")) c_forced = atoi(e);      // experiment knob (tools/prio_sweep.py)
+        if (c_forced > 0 && (uint64_t)((255 + c_forced - 1) / c_forced) * n >= (1ull << 31)) c_forced = 0;
         p.c = c_forced > 0 ? c_forced : best;
         p.W = (255 + p.c - 1) / p.c;
         p.nbuckets = 1u << (p.c - 1);

@@ -42,6 +42,9 @@ struct zkr_pkey {
     int* err = nullptr;      // device flag: witness[0] != 1 or r/s out of range
     char* rs_dev = nullptr;  // 64 B staging for (r | s)
     void* pinned = nullptr;  // 256 + 64 B pinned host staging
+    // zkr_prove_batch: second witness buffer + upload events, so that witness i+1 is uploaded while proof i runs
+    Fr* wext2 = nullptr;
+    cudaEvent_t ev_up[2] = {};
     cudaEvent_t ev[16] = {};
     size_t bytes = 0;
 };
@@ -244,6 +247,9 @@ void pkey_release(zkr_pkey* pk) {
     void* ps[] = {pk->a_ptr, pk->a_sig, pk->a_coef, pk->b_ptr, pk->b_sig, pk->b_coef, pk->wext, pk->at, pk->bt,
                   pk->st, pk->h, pk->res, pk->proof, pk->err, pk->rs_dev};
     for (void* p : ps) cudaFree(p);
+    if (pk->wext2) cudaFree(pk->wext2);
+    for (auto& e : pk->ev_up)
+        if (e) cudaEventDestroy(e);
     if (pk->pinned) cudaFreeHost(pk->pinned);
     for (auto& e : pk->ev)
         if (e) cudaEventDestroy(e);
@@ -442,23 +448,25 @@ extern "C" int zkr_pkey_info(const zkr_pkey* pk, uint32_t* n_vars, uint32_t* n_p
 }
 
 // Queue one proof: witness already in pk->wext[0..n), (r|s) in pk->rs_dev.  Result -> d_proof.
-static int prove_enqueue(zkr_ctx* ctx, const zkr_pkey* pk, char* d_proof, bool timed, zkr_comm* comm = nullptr) {
+static int prove_enqueue(zkr_ctx* ctx, const zkr_pkey* pk, char* d_proof, bool timed, zkr_comm* comm = nullptr,
+                         Fr* wext = nullptr) {
     const uint32_t n = pk->n_vars, m = pk->domain_size;
+    if (!wext) wext = pk->wext;
     cudaStream_t us = ctx->user_stream;
     cudaEvent_t const* ev = pk->ev;
-    ZKR_LAUNCH(ctx, k_prep_scalars, 1, 1, 0, us, pk->wext, n, (const Fr*)pk->rs_dev, pk->err);
-    ZKR_LAUNCH(ctx, k_witness_range, ceil_div(n, 256), 256, 0, us, pk->wext, n, pk->err);
+    ZKR_LAUNCH(ctx, k_prep_scalars, 1, 1, 0, us, wext, n, (const Fr*)pk->rs_dev, pk->err);
+    ZKR_LAUNCH(ctx, k_witness_range, ceil_div(n, 256), 256, 0, us, wext, n, pk->err);
     const bool par = !ctx->serial;
     if (par) ZKR_TRY(ctx->fork(5));
     cudaStream_t sH = par ? ctx->s[0] : us, sA = par ? ctx->s[1] : us, sB1 = par ? ctx->s[2] : us,
                  sB2 = par ? ctx->s[3] : us, sC = par ? ctx->s[4] : us;
-    const uint32_t* w = (const uint32_t*)pk->wext;
+    const uint32_t* w = (const uint32_t*)wext;
     // experiment knob (tools/prio_sweep.py): ZKR_H_FIRST=1 runs sparse LC + the NTT pipeline before any MSM starts
     const bool h_first = getenv("ZKR_H_FIRST") && atoi(getenv("ZKR_H_FIRST")) != 0;
     auto h_front = [&]() -> int {
         if (timed) cudaEventRecord(ev[0], sH);
         ZKR_LAUNCH(ctx, k_sparse_lc, dim3(ceil_div(m, 128), 2), 128, 0, sH, pk->a_ptr, pk->a_sig, pk->a_coef, pk->b_ptr,
-                   pk->b_sig, pk->b_coef, pk->wext, pk->at, pk->bt, m);
+                   pk->b_sig, pk->b_coef, wext, pk->at, pk->bt, m);
         if (timed) cudaEventRecord(ev[1], sH);
         ZKR_TRY(h_pipeline(ctx, sH, pk->at, pk->bt, pk->st, pk->h, pk->log_m, true));
         if (timed) cudaEventRecord(ev[2], sH);
@@ -495,14 +503,14 @@ static int prove_enqueue(zkr_ctx* ctx, const zkr_pkey* pk, char* d_proof, bool t
         int parity = 0;
         ZKR_TRY(comm_allgather_small(comm, us, pk->res, R_TOTAL, &parity));
         ZKR_LAUNCH(ctx, k_sum_res, 5, 1, 0, us, comm_gather_slot(comm, comm->rank, parity, 0), comm->world, pk->res);
-        ZKR_LAUNCH(ctx, k_blind_muls, 2, 32 * kBlindWarps, kBlindSmem, us, pk->res, pk->wext, n);
+        ZKR_LAUNCH(ctx, k_blind_muls, 2, 32 * kBlindWarps, kBlindSmem, us, pk->res, wext, n);
     } else {
         // the two blinding scalar multiplications need A and B1
         if (par) {
             ZKR_CUDA(cudaEventRecord(ctx->ev_join[2], sB1));
             ZKR_CUDA(cudaStreamWaitEvent(sA, ctx->ev_join[2], 0));
         }
-        ZKR_LAUNCH(ctx, k_blind_muls, 2, 32 * kBlindWarps, kBlindSmem, sA, pk->res, pk->wext, n);
+        ZKR_LAUNCH(ctx, k_blind_muls, 2, 32 * kBlindWarps, kBlindSmem, sA, pk->res, wext, n);
         if (par) ZKR_TRY(ctx->join(5));
     }
     if (timed) cudaEventRecord(ev[12], us);
@@ -610,24 +618,80 @@ extern "C" int zkr_prove_dev(zkr_ctx* ctx, const zkr_pkey* pk, const void* d_wit
     return prove_enqueue(ctx, pk, (char*)d_out_proof, false);
 }
 
+// All proofs assigned to one context, pipelined: while proof k runs, the witness of proof k+1 is uploaded into the
+// other witness buffer on the context's copy stream (s[5]); the host only waits for proof k's 256 bytes and flags.
+static int prove_batch_ctx(zkr_ctx* ctx, const zkr_pkey* pk, const void* const* witnesses, size_t n_signals,
+                           int first, int stride, int n_proofs, const void* rs32, void* out_proofs) {
+    if (!ctx || !pk || pk->ctx != ctx || pk->world != 1) {
+        set_error("zkr_prove_batch: keys[i] must be a non-sharded key loaded on ctxs[i]");
+        return ZKR_E_INVALID;
+    }
+    if (n_signals != pk->n_vars) {
+        set_error("witness has %zu signals, key expects %u", n_signals, pk->n_vars);
+        return ZKR_E_INVALID;
+    }
+    if (first >= n_proofs) return ZKR_OK;
+    DeviceGuard g(ctx->device);
+    zkr_pkey* mpk = const_cast<zkr_pkey*>(pk);
+    const size_t wbytes = 32ull * pk->n_vars;
+    if (!mpk->wext2) {
+        ZKR_CUDA(cudaMalloc((void**)&mpk->wext2, 32ull * (pk->n_vars + 4)));
+        mpk->bytes += 32ull * (pk->n_vars + 4);
+        for (auto& e : mpk->ev_up) ZKR_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    Fr* buf[2] = {pk->wext, pk->wext2};
+    cudaStream_t us = ctx->user_stream, cs = ctx->s[kNumStreams - 1];
+    char* pin = (char*)pk->pinned;
+    for (int i = first; i < n_proofs; i += stride)
+        if (!witnesses[i]) {
+            set_error("zkr_prove_batch: witnesses[%d] is null", i);
+            return ZKR_E_INVALID;
+        }
+    // everything queued on the user stream so far (a previous proof on this key) must be done with buf[0]
+    ZKR_CUDA(cudaStreamSynchronize(us));
+    ZKR_CUDA(cudaMemcpyAsync(buf[0], witnesses[first], wbytes, cudaMemcpyHostToDevice, cs));
+    ZKR_CUDA(cudaEventRecord(pk->ev_up[0], cs));
+    int k = 0;
+    for (int i = first; i < n_proofs; i += stride, k++) {
+        const int cur = k & 1;
+        memset(pin + 256, 0, 64);
+        if (rs32) memcpy(pin + 256, (const char*)rs32 + 64ull * i, 64);
+        ZKR_CUDA(cudaStreamWaitEvent(us, pk->ev_up[cur], 0));
+        ZKR_CUDA(cudaMemcpyAsync(pk->rs_dev, pin + 256, 64, cudaMemcpyHostToDevice, us));
+        ZKR_TRY(prove_enqueue(ctx, pk, pk->proof, false, nullptr, buf[cur]));
+        ZKR_CUDA(cudaMemcpyAsync(pin, pk->proof, ZKR_PROOF_BYTES, cudaMemcpyDeviceToHost, us));
+        if (i + stride < n_proofs) {      // proof k-1, the last reader of buf[cur ^ 1], was waited for below
+            ZKR_CUDA(cudaMemcpyAsync(buf[cur ^ 1], witnesses[i + stride], wbytes, cudaMemcpyHostToDevice, cs));
+            ZKR_CUDA(cudaEventRecord(pk->ev_up[cur ^ 1], cs));
+        }
+        ZKR_CUDA(cudaStreamSynchronize(us));
+        int rc = check_range_flags(ctx, pk);
+        if (rc != ZKR_OK) {
+            cudaStreamSynchronize(cs);
+            return rc;
+        }
+        memcpy((char*)out_proofs + (size_t)ZKR_PROOF_BYTES * i, pin, ZKR_PROOF_BYTES);
+    }
+    ZKR_CUDA(cudaStreamSynchronize(cs));
+    return ZKR_OK;
+}
+
 extern "C" int zkr_prove_batch(zkr_ctx* const* ctxs, const zkr_pkey* const* pks, int n_ctx,
                                const void* const* witnesses, size_t n_signals, int n_proofs, const void* rs32,
                                void* out_proofs) {
-    if (!ctxs || !pks || n_ctx < 1 || !witnesses || n_proofs < 0 || !out_proofs) return ZKR_E_INVALID;
+    if (!ctxs || !pks || n_ctx < 1 || (!witnesses && n_proofs) || n_proofs < 0 || (!out_proofs && n_proofs)) return ZKR_E_INVALID;
     std::vector<int> rcs(n_ctx, ZKR_OK);
     std::vector<std::string> msgs(n_ctx);
+    if (n_ctx == 1) {
+        return prove_batch_ctx(ctxs[0], pks[0], witnesses, n_signals, 0, 1, n_proofs, rs32, out_proofs);
+    }
     std::vector<std::thread> th;
     for (int c = 0; c < n_ctx; c++) {
         th.emplace_back([&, c]() {
-            for (int i = c; i < n_proofs; i += n_ctx) {
-                const char* rs = rs32 ? (const char*)rs32 + 64ull * i : nullptr;
-                int rc = zkr_prove(ctxs[c], pks[c], witnesses[i], n_signals, rs, rs ? rs + 32 : nullptr,
-                                   (char*)out_proofs + (size_t)ZKR_PROOF_BYTES * i, nullptr);
-                if (rc != ZKR_OK) {
-                    rcs[c] = rc;
-                    msgs[c] = zkr_last_error();
-                    return;
-                }
+            int rc = prove_batch_ctx(ctxs[c], pks[c], witnesses, n_signals, c, n_ctx, n_proofs, rs32, out_proofs);
+            if (rc != ZKR_OK) {
+                rcs[c] = rc;
+                msgs[c] = zkr_last_error();
             }
         });
     }

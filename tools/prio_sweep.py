@@ -16,9 +16,8 @@ from simple_zk_rollups_b200 import _lib, keygen, prover, synth  # noqa: E402
 TOXIC = (0x1234567890ABCDEF1234567890ABCDEF1234567, 0x2222222222222222222222222222222222221,
          0x3333333333333333333333333333333333333331, 0x44444444444444444444444444444444441,
          0x555555555555555555555555555555555555555551)
-CONFIGS = {"equal": "0,0,0,0,0,0", "b2_highest_h_high": "-1,0,0,-2,0,0", "ab_high": "0,-1,-1,0,0,0",
-           "ab_highest_b2_h_high": "-1,-2,-2,-1,0,0", "ab_b2_high": "0,-1,-1,-1,0,0", "b2_highest_ab_h_high": "-1,-1,-1,-2,0,0",
-           "ab_highest_h_high": "-1,-2,-2,0,0,0", "ab_highest_b2_high": "0,-2,-2,-1,0,0", "all_but_c_high": "-1,-1,-1,-1,0,0"}
+CONFIGS = {"equal": "0,0,0,0,0,0", "c16": "0,0,0,0,0,0;C16", "c18": "0,0,0,0,0,0;C18", "c19": "0,0,0,0,0,0;C19",
+           "c20": "0,0,0,0,0,0;C20", "c21": "0,0,0,0,0,0;C21"}
 
 
 def main():
@@ -40,6 +39,7 @@ def main():
         os.environ["ZKR_STREAM_PRIO"] = prio.split(";")[0]
         os.environ["ZKR_H_FIRST"] = "1" if prio.endswith(";H") else "0"
         os.environ["ZKR_LEVEL_LOG_BIG"] = prio.split(";L")[1] if ";L" in prio else "0"
+        os.environ["ZKR_MSM_C"] = prio.split(";C")[1] if ";C" in prio else "0"
         gp = prover.Groth16Prover(0)
         L = gp.L
         key = gp.load_key(pk_bin)
