@@ -363,10 +363,13 @@ def run_reference(args):
         print(json.dumps({"impl": "reference", "unavailable": "no proving key for the workload (needs a GPU to run the synthetic setup)"}))
         return
     rs = (0x1F2E3D4C5B6A79881122334455667788 << 64 | 0x99AABBCCDDEEFF00, 0x0123456789ABCDEF << 100 | 77)
+    mode = args.ref_mode
+    if args.ref_threads:
+        cores = args.ref_threads
     times = []
     for i in range(args.warmup + args.steps):
         t0 = time.time()
-        cbind.prove(pk_bin, wbytes, rs[0], rs[1], mode=1, threads=cores)
+        cbind.prove(pk_bin, wbytes, rs[0], rs[1], mode=mode, threads=cores)
         dt = time.time() - t0
         if i >= args.warmup:
             times.append(dt)
@@ -385,7 +388,9 @@ def run_reference(args):
                    "baseline_config": BASELINE_CONFIG.get(args.shape, "BASELINE.json configs[1] shape family")},
         "cpu_baseline": {"value": round(val, 5), "unit": "proofs/s", "cores": cores, "kind": "port",
                          "sample": "every step is 1 full proof of the workload (C restatement of websnark groth16GenProof: "
-                                   "Pippenger multiexp + iterative NTT on all host threads)"},
+                                   + ("Pippenger multiexp + iterative NTT" if mode == 1 else
+                                      "snarkjs arithmetic structure: one double-and-add multiplication per point, recursive radix-2 FFT")
+                                   + ", %d host thread(s))" % cores},
         "e2e": {"value": round(val, 5), "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }), flush=True)
@@ -398,6 +403,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--shape", default="tx_2p20", help="withdraw | tx | tx_2p20 | tx_2p22 (simple_zk_rollups_b200.synth.SHAPES)")
+    ap.add_argument("--ref-mode", type=int, default=1, choices=[0, 1],
+                    help="--impl reference: 1 = Pippenger + iterative NTT (default), 0 = snarkjs arithmetic structure (SURVEY 8(d) CPU-A)")
+    ap.add_argument("--ref-threads", type=int, default=0, help="--impl reference: host threads (default: all)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs under ncu)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

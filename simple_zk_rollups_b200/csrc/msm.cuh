@@ -7,17 +7,19 @@
 //   * The bases are static per circuit, HBM is 180 GB: at key-load time every base P_i is expanded
 //     to its W window multiples 2^(c w) P_i (affine, Montgomery).  All windows then share ONE set of
 //     2^(c-1) buckets, there is no window-combine (no 254 serial doublings), and c can be larger
-//     than a per-window scheme allows (c = 20 at n = 2^20 -> 13 mixed adds per point instead of 16).
+//     than a per-window scheme allows (c = 17 at n = 2^20 -> 15 mixed adds per point, c = 20 at 2^22 -> 13).
 //   * per MSM:  digits (signed, c bits)  ->  radix sort of (bucket, point-ref) pairs  ->
-//     chunked bucket accumulation  ->  block-level weighted bucket reduction.
+//     chunked bucket accumulation  ->  boundary levels  ->  parallel weighted bucket reduction.
 //   * accumulation is perfectly load balanced for ANY scalar distribution: thread t owns entries
 //     [tL, (t+1)L) of the bucket-sorted list, adds runs of equal bucket with XYZZ mixed adds, writes
 //     complete (interior) runs straight to their bucket and hands its first / last partial run to the
 //     next level, which applies the same algorithm to the (<= 2 per thread) boundary partials.  A
 //     bucket holding 3 % of all points (the {0,1} witness skew of the rollup circuit) simply spans
 //     many threads.
-//   * reduction sum_b (b+1) B_b: per-thread running sums over K consecutive buckets, then a block
-//     suffix-scan turns sum_l l*S_l into plain sums; one more single-block kernel finishes.
+//   * reduction sum_b (b+1) B_b without a serial running sum: row / column sums of the bucket array viewed as a
+//     2^lr x 2^lc matrix, then bit-decomposed weighted sums (k_bucket_sums / k_bucket_weighted below).
+//   * measured dead end: capping the G2 accumulation kernel at 168 / 128 registers (3 / 4 CTAs per SM instead of 2,
+//     ~90 / ~270 spilled words per addition) makes the 2^20 proof slower, 17.8 / 18.3 ms against 17.3 ms.
 #pragma once
 #include <cstdlib>
 

@@ -16,8 +16,11 @@ from simple_zk_rollups_b200 import _lib, keygen, prover, synth  # noqa: E402
 TOXIC = (0x1234567890ABCDEF1234567890ABCDEF1234567, 0x2222222222222222222222222222222222221,
          0x3333333333333333333333333333333333333331, 0x44444444444444444444444444444444441,
          0x555555555555555555555555555555555555555551)
-CONFIGS = {"equal": "0,0,0,0,0,0", "c16": "0,0,0,0,0,0;C16", "c18": "0,0,0,0,0,0;C18", "c19": "0,0,0,0,0,0;C19",
-           "c20": "0,0,0,0,0,0;C20", "c21": "0,0,0,0,0,0;C21"}
+# name -> "p0,..,p5[;H][;Ln][;Cn]": stream priorities, H = NTT pipeline before the MSMs, Ln = boundary-level granularity,
+# Cn = forced MSM window size.  Results of the round-1 sweeps: profiles/r01_sched_sweep.json, r01_window_sweep.json.
+CONFIGS = {"equal": "0,0,0,0,0,0", "b2_highest_h_high": "-1,0,0,-2,0,0", "ab_high": "0,-1,-1,0,0,0",
+           "b2_highest_ab_h_high": "-1,-1,-1,-2,0,0", "all_but_c_high": "-1,-1,-1,-1,0,0", "h_first": "0,0,0,0,0,0;H",
+           "lvl4": "0,0,0,0,0,0;L4", "c16": "0,0,0,0,0,0;C16", "c19": "0,0,0,0,0,0;C19"}
 
 
 def main():
