@@ -12,6 +12,7 @@ reference; circom cannot run here, so the witness calculator is an injected call
 No CPU fallback: every prove goes through the CUDA library or raises.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -186,6 +187,16 @@ def genProof(provingKey, witness, r=None, s=None, prover=None, _key_cache={}):
     return {"proof": proof_from_bytes(buf), "publicSignals": [str(int(x)) for x in witness[1:n_public + 1]]}
 
 
+def _load_any_key(p, provingKey):
+    """snarkjs pk JSON as dict, as JSON text or as a path to proving_key.json (the reference `require`s the file,
+    operator/src/snarks/tx.ts:3), or an already binarified key (bytes / uint8 array)."""
+    if isinstance(provingKey, dict):
+        return p.load_key(binarifyProvingKey(provingKey))
+    if isinstance(provingKey, str):
+        return p.load_key_json(open(provingKey).read() if os.path.exists(provingKey) else provingKey)
+    return p.load_key(provingKey)
+
+
 def createProofGenerator(provingKey, verifyingKey, circuitName, calculateWitness, isValid=None, prover=None):
     """Mirror of operator/src/snarks/common.ts:10-53.
 
@@ -198,7 +209,9 @@ def createProofGenerator(provingKey, verifyingKey, circuitName, calculateWitness
         pass verifyingKey=None to skip the self-check.
     The returned callable is synchronous; the reference's is async only because websnark is."""
     p = prover or default_prover()
-    key = p.load_key(binarifyProvingKey(provingKey) if isinstance(provingKey, dict) else provingKey)
+    key = _load_any_key(p, provingKey)
+    if isinstance(verifyingKey, str) and os.path.exists(verifyingKey):
+        verifyingKey = open(verifyingKey).read()
     if isValid is None and verifyingKey is not None:
         vkey = p.load_vkey(verifyingKey)             # once per circuit; IC tables resident on the GPU
 
@@ -225,3 +238,13 @@ def createProofGenerator(provingKey, verifyingKey, circuitName, calculateWitness
         }
 
     return generate
+
+
+def bindCircuit(buildDir, name, calculateWitness, prover=None):
+    """Mirror of the reference's thin binders (operator/src/snarks/tx.ts:1-10, withdraw.ts:1-10):
+        genTxVerifierProof       = bindCircuit(build, "tx", calc)        # txProvingKey.json / txVerifyingKey.json
+        genWithdrawVerifierProof = bindCircuit(build, "withdraw", calc)  # withdrawProvingKey.json / ...
+    buildDir is the reference's prover/build directory; the key files are parsed natively, once."""
+    return createProofGenerator(os.path.join(buildDir, "%sProvingKey.json" % name),
+                                os.path.join(buildDir, "%sVerifyingKey.json" % name),
+                                "%s.circom" % name, calculateWitness, prover=prover)

@@ -155,6 +155,28 @@ def test_prove_from_json_text(gp):
     assert ei.value.code == -2
 
 
+def test_bind_circuit_from_build_directory(gp, tmp_path):
+    """tx.ts / withdraw.ts shape: keys come from prover/build/<name>{Proving,Verifying}Key.json files; the generator
+    parses them natively once, proves, self-checks with zkr_verify and formats the Solidity call data."""
+    import json
+    r1, w = synth.generate(70, 3, seed=17)
+    pk, vk, _ = g.setup(r1.to_dicts(), TOXIC)
+    (tmp_path / "withdrawProvingKey.json").write_text(json.dumps(bf.pk_to_json(pk)))
+    (tmp_path / "withdrawVerifyingKey.json").write_text(json.dumps(bf.vk_to_json(vk)))
+    seen = {}
+
+    def calc(name, inputs):
+        seen["name"] = name
+        return w, 3
+
+    gen = prover.bindCircuit(str(tmp_path), "withdraw", calc, prover=gp)
+    out = gen({"x": 1}, r=21, s=22)
+    assert seen["name"] == "withdraw.circom"
+    assert bf.proof_from_json(out["proof"]) == g.gen_proof(pk, w, 21, 22)[0]
+    assert out["solidityProof"]["inputs"] == [str(x) for x in w[1:4]]
+    assert out["solidityProof"]["b"][0] == [out["proof"]["pi_b"][0][1], out["proof"]["pi_b"][0][0]]
+
+
 def test_prove_batch_round_robin(gp):
     """zkr_prove_batch over two contexts (two GPUs when present, else two contexts on device 0): every proof of the
     batch equals the oracle's for its own witness and (r, s), in input order; a bad witness fails the call."""
