@@ -135,6 +135,13 @@ struct XYZZ {
         F iz2 = iz3.sqr() * zz.sqr();
         return {x * iz2, y * iz3};
     }
+    // same, with the variable-time inversion of fp_inv.cuh: single-thread tails only (k_finish)
+    __device__ __forceinline__ Affine<F> to_affine_vartime() const {
+        if (is_inf()) return {F::zero(), F::zero()};
+        F iz3 = zzz.inverse_vartime();
+        F iz2 = iz3.sqr() * zz.sqr();
+        return {x * iz2, y * iz3};
+    }
 };
 
 using G1Affine = Affine<Fq>;

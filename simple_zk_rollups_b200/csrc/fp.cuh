@@ -12,6 +12,8 @@
 #pragma once
 #include <cstdint>
 
+#include "fp_inv.cuh"
+
 namespace zkr {
 
 struct FqParams {   // base field q (binarify.ts:80)
@@ -301,6 +303,15 @@ struct Fp {
         }
         return acc;
     }
+    // Same result as inverse(), by the binary extended Euclid of fp_inv.cuh (variable time, no multiplier): for the
+    // O(1) inversions that run on ONE thread at the very end of a proof (k_finish).  Not for full grids: the data-
+    // dependent loops would diverge.  binary_inverse works on plain integers: (aR)^-1 = a^-1 R^-1, and two
+    // Montgomery products with R^2 bring it back to a^-1 R.
+    __device__ __forceinline__ Fp inverse_vartime() const {
+        Fp t;
+        binary_inverse<P>(t.v, v);
+        return (t * r2()) * r2();
+    }
     // is the standard-form value < p ?
     __device__ __forceinline__ bool in_range() const {
         uint32_t t[8];
@@ -364,6 +375,10 @@ struct Fq2 {
     __device__ __forceinline__ Fq2 dbl() const { return {c0.dbl(), c1.dbl()}; }
     __device__ __forceinline__ Fq2 inverse() const {
         Fq n = (c0.sqr() + c1.sqr()).inverse();
+        return {c0 * n, (c1 * n).neg()};
+    }
+    __device__ __forceinline__ Fq2 inverse_vartime() const {   // see Fp::inverse_vartime
+        Fq n = (c0.sqr() + c1.sqr()).inverse_vartime();
         return {c0 * n, (c1 * n).neg()};
     }
     __device__ __forceinline__ Fq2 to_mont() const { return {c0.to_mont(), c1.to_mont()}; }

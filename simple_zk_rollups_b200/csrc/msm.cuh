@@ -430,10 +430,11 @@ k_bucket_weighted(XYZZ<F>* __restrict__ sums, int lr, int lc, unsigned int* __re
     }
 }
 
-// XYZZ (Montgomery) -> affine standard form bytes; identity -> zeros
+// XYZZ (Montgomery) -> affine standard form bytes; identity -> zeros.  One thread at the tail of a standalone MSM:
+// the variable-time inversion (fp_inv.cuh) is the whole kernel.
 template <class F>
 __global__ void k_xyzz_to_affine_std(const XYZZ<F>* in, char* out) {
-    Affine<F> a = XYZZ<F>::load(in).to_affine();
+    Affine<F> a = XYZZ<F>::load(in).to_affine_vartime();
     a.x.from_mont().store(out);
     a.y.from_mont().store(out + sizeof(F));
 }

@@ -104,23 +104,58 @@ k_ntt_pass(Fr* __restrict__ data, int k, int c, int s, int ls_, int chunk_log, u
     const unsigned c0 = ctw + cm;            // ... and in the transform's global coordinates
     const int cmask = (1 << c) - 1;
 
-    // ---- global -> shared, 16-byte units
-    for (int u = tid; u < 2 * tile; u += blockDim.x) {
-        int e = u >> 1, half = u & 1;
-        int row = e >> c, col = e & cmask;
-        const uint4* src = reinterpret_cast<const uint4*>(chunk + ((size_t)row << ls) + cm + col) + half;
-        uint4 v = *src;
-        uint32_t* d = sm + (4 * half) * plane + slot_of(e);
-        d[0] = v.x;
-        d[plane] = v.y;
-        d[2 * plane] = v.z;
-        d[3 * plane] = v.w;
+    const unsigned lbmask = (1u << lb) - 1;
+    // ---- global -> shared.  blockDim.x == tile / 8 (launch_pass), so every thread moves exactly 8 elements = 16
+    // 16-byte units; the loads of a group are all issued before the first shared store (an un-unrolled loop exposed
+    // one HBM latency per unit: 12 % of the pass in the round-1 ncu source view, profiles/r01_ncu_ntt_pass.md).
+    if (DIT && s > 0) {
+        // DIT applies the inter-pass twiddle omega_N'^(col * rev(row)) BEFORE its butterflies: do it on the way in,
+        // whole elements per thread, so the register stages below hold nothing but the 8 butterfly operands
+        // (with the twiddle inside the first stage ptxas spilled 272 B per thread).
+#pragma unroll 1
+        for (int g = 0; g < 2; g++) {
+            Fr v[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int e = tid + (g * 4 + i) * (tile >> 3);
+                v[i] = Fr::load(chunk + ((size_t)(e >> c) << ls) + cm + (e & cmask));
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int e = tid + (g * 4 + i) * (tile >> 3);
+                const unsigned rev = __brev((unsigned)(e >> c)) >> (32 - k);
+                const unsigned X = ((c0 + (e & cmask)) * rev) << tw_shift;
+                const Fr t = Fr::load_ro(tlo + (X & lbmask)) * Fr::load_ro(thi + (X >> lb));
+                v[i] = v[i] * t;
+                uint32_t* d = sm + slot_of(e);
+#pragma unroll
+                for (int l = 0; l < 8; l++) d[l * plane] = v[i].v[l];
+            }
+        }
+    } else {
+#pragma unroll 1
+        for (int g = 0; g < 2; g++) {
+            uint4 v[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int u = tid + (g * 8 + i) * (tile >> 3);
+                const int e = u >> 1;
+                v[i] = *(reinterpret_cast<const uint4*>(chunk + ((size_t)(e >> c) << ls) + cm + (e & cmask)) + (u & 1));
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int u = tid + (g * 8 + i) * (tile >> 3);
+                uint32_t* d = sm + (4 * (u & 1)) * plane + slot_of(u >> 1);
+                d[0] = v[i].x;
+                d[plane] = v[i].y;
+                d[2 * plane] = v[i].z;
+                d[3 * plane] = v[i].w;
+            }
+        }
     }
     __syncthreads();
 
-    const unsigned lbmask = (1u << lb) - 1;
     int bit = DIT ? c : T - 1;
-    bool first = true;
     while (DIT ? (bit <= T - 1) : (bit >= c)) {
         int lo, act_lo, act_hi;
         if (DIT) {
@@ -140,18 +175,7 @@ k_ntt_pass(Fr* __restrict__ data, int k, int c, int s, int ls_, int chunk_log, u
 #pragma unroll
             for (int l = 0; l < 8; l++) x[j].v[l] = p[l * plane];
         }
-        const bool tw_now = (s > 0) && (DIT ? first : (act_lo == c));
-        if (DIT && tw_now) {
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                int e = base + (j << lo);
-                unsigned rho = e >> c, col = e & cmask;
-                unsigned rev = __brev(rho) >> (32 - k);
-                unsigned X = ((c0 + col) * rev) << tw_shift;
-                Fr t = Fr::load_ro(tlo + (X & lbmask)) * Fr::load_ro(thi + (X >> lb));
-                x[j] = x[j] * t;
-            }
-        }
+        const bool tw_now = !DIT && (s > 0) && (act_lo == c);     // DIF: after the last butterfly level (DIT: at load)
 #pragma unroll
         for (int ii = 0; ii < 3; ii++) {
             const int i = DIT ? ii : 2 - ii;
@@ -170,8 +194,8 @@ k_ntt_pass(Fr* __restrict__ data, int k, int c, int s, int ls_, int chunk_log, u
                     const int j0 = jl | (ju << (i + 1));
                     const int j1 = j0 | (1 << i);
                     if (DIT) {
-                        Fr v = pc > 0 ? x[j1] * w : x[j1];
-                        Fr u = x[j0];
+                        if (pc > 0) x[j1] = x[j1] * w;
+                        const Fr u = x[j0], v = x[j1];
                         x[j0] = u + v;
                         x[j1] = u - v;
                     } else {
@@ -201,7 +225,6 @@ k_ntt_pass(Fr* __restrict__ data, int k, int c, int s, int ls_, int chunk_log, u
             for (int l = 0; l < 8; l++) p[l * plane] = x[j].v[l];
         }
         __syncthreads();
-        first = false;
         bit = DIT ? act_hi + 1 : act_lo - 1;
     }
 
@@ -426,6 +449,7 @@ int ntt_run(zkr_ctx* ctx, cudaStream_t st, Fr* data, int log_n, bool dit, bool i
     int ks[4];
     const int np = plan_passes(log_n, ks);
     const NttXchg none = {};
+    static const unsigned min_blocks = getenv("ZKR_NTT_MIN_BLOCKS") ? (unsigned)atoi(getenv("ZKR_NTT_MIN_BLOCKS")) : 1024u;   // experiment knob; 0 = full-width tiles always
     for (int step = 0; step < np; step++) {
         const int i = dit ? np - 1 - step : step;
         PassGeom g;
@@ -435,6 +459,10 @@ int ntt_run(zkr_ctx* ctx, cudaStream_t st, Fr* data, int log_n, bool dit, bool i
         g.s = g.chunk_log - g.k;
         g.c = kTileLog - g.k;
         if (g.c > g.s) g.c = g.s;
+        // Transforms of <= 2^20 elements make fewer full-width tiles than the machine has CTA slots (2^17: 64 tiles for
+        // 148 SMs; 2^20: 512 tiles for 296 slots = 1.73 waves): narrower tiles spread the same threads over all SMs.
+        // The pass is IMAD-bound with DRAM at 2-4 % of peak, so the shorter contiguous segments cost nothing.
+        while (g.c > 0 && (1u << (log_n - g.k - g.c)) < min_blocks) g.c--;
         g.ls = g.s;
         g.ctw = 0;
         g.tw_shift = log_n - g.chunk_log;

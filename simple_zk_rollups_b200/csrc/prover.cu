@@ -148,20 +148,24 @@ __global__ void __launch_bounds__(32 * kBlindWarps) k_blind_muls(char* res, cons
 constexpr size_t kBlindSmem = sizeof(G1XYZZ) * (256 + kBlindWarps);
 
 // block 0: pi_a, block 1: pi_b, block 2: pi_c = C + H + T1 + T2; affine, standard form
-__global__ void k_finish(const char* res, char* proof) {
+// Three single-thread blocks, nothing left to overlap them: the inversion is the whole kernel.  fermat == 0 (default)
+// uses the binary extended Euclid of fp_inv.cuh, fermat != 0 the a^(p-2) ladder (ZKR_FINISH_FERMAT=1, for A/B timing).
+__global__ void k_finish(const char* res, char* proof, int fermat) {
     if (blockIdx.x == 0) {
-        G1Affine a = G1XYZZ::load(res + R_A).to_affine();
+        const G1XYZZ p = G1XYZZ::load(res + R_A);
+        G1Affine a = fermat ? p.to_affine() : p.to_affine_vartime();
         a.x.from_mont().store(proof);
         a.y.from_mont().store(proof + 32);
     } else if (blockIdx.x == 1) {
-        G2Affine a = G2XYZZ::load(res + R_B2).to_affine();
+        const G2XYZZ p = G2XYZZ::load(res + R_B2);
+        G2Affine a = fermat ? p.to_affine() : p.to_affine_vartime();
         a.x.from_mont().store(proof + 64);
         a.y.from_mont().store(proof + 128);
     } else {
         G1XYZZ c = G1XYZZ::load(res + R_C);
 #pragma unroll 1
         for (int i = 0; i < 3; i++) c.add(G1XYZZ::load(res + (i == 0 ? R_H : (i == 1 ? R_T1 : R_T2))));
-        G1Affine a = c.to_affine();
+        G1Affine a = fermat ? c.to_affine() : c.to_affine_vartime();
         a.x.from_mont().store(proof + 192);
         a.y.from_mont().store(proof + 224);
     }
@@ -514,7 +518,8 @@ static int prove_enqueue(zkr_ctx* ctx, const zkr_pkey* pk, char* d_proof, bool t
         if (par) ZKR_TRY(ctx->join(5));
     }
     if (timed) cudaEventRecord(ev[12], us);
-    ZKR_LAUNCH(ctx, k_finish, 3, 1, 0, us, (const char*)pk->res, d_proof);
+    static const int finish_fermat = getenv("ZKR_FINISH_FERMAT") ? atoi(getenv("ZKR_FINISH_FERMAT")) : 0;   // experiment knob
+    ZKR_LAUNCH(ctx, k_finish, 3, 1, 0, us, (const char*)pk->res, d_proof, finish_fermat);
     if (timed) cudaEventRecord(ev[13], us);
     return ZKR_OK;
 }
