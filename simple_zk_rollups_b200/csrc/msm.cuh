@@ -564,15 +564,12 @@ int bases_build(zkr_ctx* ctx, zkr_bases* b, const char* h_points, size_t n_src, 
     ZKR_CUDA(cudaMemsetAsync(wk.range_err, 0, sizeof(int), st));
     wk.bytes += wk.cub_bytes + XB * ((size_t)b->plan.nbuckets + bnd0 + bnd1 + nred + 1) + 4 * (bnd0 + bnd1);
     b->bytes += wk.bytes;
-    static bool attr_done[2] = {false, false};
-    const int which = sizeof(F) == 32 ? 0 : 1;
-    if (!attr_done[which]) {
-        ZKR_CUDA(cudaFuncSetAttribute(k_bucket_sums<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(XB * kReduceThreads)));
-        ZKR_CUDA(cudaFuncSetAttribute(k_bucket_weighted<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(XB * kReduceThreads)));
-        ZKR_CUDA(cudaFuncSetAttribute((k_accum_affine<F, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
-        ZKR_CUDA(cudaFuncSetAttribute((k_accum_affine<F, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
-        attr_done[which] = true;
-    }
+    // per device, so once per work-buffer allocation rather than once per process (cold path, idempotent): a process
+    // that drives several GPUs must opt in to > 48 KB of dynamic shared memory on each of them
+    ZKR_CUDA(cudaFuncSetAttribute(k_bucket_sums<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(XB * kReduceThreads)));
+    ZKR_CUDA(cudaFuncSetAttribute(k_bucket_weighted<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(XB * kReduceThreads)));
+    ZKR_CUDA(cudaFuncSetAttribute((k_accum_affine<F, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+    ZKR_CUDA(cudaFuncSetAttribute((k_accum_affine<F, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
     ZKR_CUDA(cudaStreamSynchronize(st));
     return ZKR_OK;
 }

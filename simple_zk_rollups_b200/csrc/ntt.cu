@@ -372,14 +372,15 @@ int ntt_get_tables(zkr_ctx* ctx, int log_n, NttTables** out) {
         set_error("NTT size 2^%d unsupported (1..27)", log_n);
         return ZKR_E_UNSUPPORTED;
     }
-    static bool attr_done = false;
-    if (!attr_done) {
+    // Function attributes are per device: set them whenever tables are built for a context (cold path, idempotent).
+    // A process-wide "done" flag left the > 48 KB opt-in missing on every device but the first one a process used
+    // (one process driving several GPUs: zkr_prove_batch / ProofQueue).
+    {
         ZKR_CUDA(cudaFuncSetAttribute((k_ntt_pass<false, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         ZKR_CUDA(cudaFuncSetAttribute((k_ntt_pass<true, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         ZKR_CUDA(cudaFuncSetAttribute((k_ntt_pass<false, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         ZKR_CUDA(cudaFuncSetAttribute((k_ntt_pass<true, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         ZKR_CUDA(cudaFuncSetAttribute((k_ntt_pass<true, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        attr_done = true;
     }
     NttTables* t = new NttTables();
     t->log_n = log_n;
