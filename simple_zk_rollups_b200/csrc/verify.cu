@@ -13,11 +13,13 @@
 //   * the pairing product is O(1) work with no data parallelism (4 Miller loops sharing one accumulator, one
 //     final exponentiation): it runs on the host core that issued the call, 4 x 64-bit Montgomery limbs,
 //     ~2 ms, while the GPU is free for the next proof.  Same split as the reference (pairings on the CPU).
-// Fq12 = Fq2[w]/(w^6 - xi), xi = 9 + u; optimal-ate Miller loop over 6x+2 with affine twist points (the
-// inversions of all pairs are batched per step), two Frobenius line additions, final exponentiation with the
-// BN hard part of Scott et al. (exponentiations by x, Frobenius maps).
+// Fq12 = Fq2[w]/(w^6 - xi), xi = 9 + u; optimal-ate Miller loop over 6x+2 with the twist points in homogeneous
+// projective coordinates (no inversion in the loop; the first, affine version with per-step batched inversions is
+// kept behind ZKR_PAIRING_AFFINE=1 as a cross-check), two Frobenius line additions, final exponentiation with the
+// BN hard part of Scott et al. (exponentiations by x with cyclotomic squarings, Frobenius maps).
 #include <immintrin.h>
 
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -266,13 +268,52 @@ Fq12 f12_mul(const Fq12& a, const Fq12& b) {
     for (int k = 0; k < 6; k++) r.c[k] = k < 5 ? add(t[k], mul_xi(t[k + 6])) : t[k];
     return r;
 }
-inline Fq12 f12_sqr(const Fq12& a) { return f12_mul(a, a); }
+// Squaring over the quadratic tower Fq12 = Fq6[w]/(w^2 - v), Fq6 = Fq2[v]/(v^3 - xi), v = w^2: with a = E + O w
+// (E = c0 + c2 v + c4 v^2, O = c1 + c3 v + c5 v^2),  a^2 = (E^2 + v O^2) + 2 E O w  and
+// E^2 + v O^2 = (E + O)(E + v O) - E O - v E O: two Fq6 products (12 Fq2 multiplications) instead of 18.
+inline void f6_mul(const Fq2* a, const Fq2* b, Fq2* r) {      // in Fq2[v]/(v^3 - xi)
+    Fq2 c[5];
+    poly3_mul(a, b, c);
+    r[0] = add(c[0], mul_xi(c[3]));
+    r[1] = add(c[1], mul_xi(c[4]));
+    r[2] = c[2];
+}
+Fq12 f12_sqr(const Fq12& a) {
+    const Fq2 E[3] = {a.c[0], a.c[2], a.c[4]}, O[3] = {a.c[1], a.c[3], a.c[5]};
+    const Fq2 vO[3] = {mul_xi(O[2]), O[0], O[1]};             // v * O
+    const Fq2 s1[3] = {add(E[0], O[0]), add(E[1], O[1]), add(E[2], O[2])};
+    const Fq2 s2[3] = {add(E[0], vO[0]), add(E[1], vO[1]), add(E[2], vO[2])};
+    Fq2 eo[3], m[3];
+    f6_mul(E, O, eo);
+    f6_mul(s1, s2, m);
+    const Fq2 veo[3] = {mul_xi(eo[2]), eo[0], eo[1]};
+    Fq12 r;
+    for (int i = 0; i < 3; i++) {
+        r.c[2 * i] = sub(sub(m[i], eo[i]), veo[i]);
+        r.c[2 * i + 1] = dbl(eo[i]);
+    }
+    return r;
+}
 // a * (l0 + l1 w + l3 w^3), l0 in Fq
 Fq12 f12_mul_line(const Fq12& a, const Fq& l0, const Fq2& l1, const Fq2& l3) {
     Fq2 t[9];
     for (int i = 0; i < 9; i++) t[i] = kZero2;
     for (int i = 0; i < 6; i++) {
         t[i] = add(t[i], mul_fq(a.c[i], l0));
+        t[i + 1] = add(t[i + 1], mul(a.c[i], l1));
+        t[i + 3] = add(t[i + 3], mul(a.c[i], l3));
+    }
+    Fq12 r;
+    for (int k = 0; k < 6; k++) r.c[k] = k < 3 ? add(t[k], mul_xi(t[k + 6])) : t[k];
+    return r;
+}
+// a * (l0 + l1 w + l3 w^3), l0 in Fq2 (projective Miller loop: the line is scaled by an Fq2 factor, which the
+// final exponentiation removes)
+Fq12 f12_mul_line2(const Fq12& a, const Fq2& l0, const Fq2& l1, const Fq2& l3) {
+    Fq2 t[9];
+    for (int i = 0; i < 9; i++) t[i] = kZero2;
+    for (int i = 0; i < 6; i++) {
+        t[i] = add(t[i], mul(a.c[i], l0));
         t[i + 1] = add(t[i + 1], mul(a.c[i], l1));
         t[i + 3] = add(t[i + 3], mul(a.c[i], l3));
     }
@@ -312,10 +353,47 @@ Fq12 f12_inv(const Fq12& a) {
     for (int i = 0; i < 6; i++) out.c[i] = mul_fq(rr.c[i], ninv);
     return out;
 }
+// Squaring in the cyclotomic subgroup G_{Phi_6(q^2)} (every value after the easy part of the final exponentiation):
+// Granger, Scott, "Faster squaring in the cyclotomic subgroup of sixth degree extensions".  View Fq12 as
+// Fq4[w]/(w^3 - s), Fq4 = Fq2[s]/(s^2 - xi), s = w^3:  a = A + B w + C w^2 with A = c0 + c3 s, B = c1 + c4 s, C = c2 + c5 s;
+//   a^2 = (3 A^2 - 2 conj(A)) + (3 s C^2 + 2 conj(B)) w + (3 B^2 - 2 conj(C)) w^2,   conj(x0 + x1 s) = x0 - x1 s.
+// 3 Fq4 squarings = 9 Fq2 squarings instead of the 12 Fq2 multiplications of f12_sqr.
+inline void f4_sqr(const Fq2& x0, const Fq2& x1, Fq2& y0, Fq2& y1) {
+    const Fq2 a = sqr(x0), b = sqr(x1);
+    y1 = sub(sub(sqr(add(x0, x1)), a), b);
+    y0 = add(a, mul_xi(b));
+}
+inline Fq2 triple(const Fq2& a) { return add(dbl(a), a); }
+Fq12 f12_cyc_sqr(const Fq12& a) {
+    Fq2 a0, a1, b0, b1, c0, c1;
+    f4_sqr(a.c[0], a.c[3], a0, a1);       // A^2
+    f4_sqr(a.c[1], a.c[4], b0, b1);       // B^2
+    f4_sqr(a.c[2], a.c[5], c0, c1);       // C^2,  s C^2 = xi c1 + c0 s
+    Fq12 r;
+    r.c[0] = sub(triple(a0), dbl(a.c[0]));
+    r.c[3] = add(triple(a1), dbl(a.c[3]));
+    r.c[1] = add(triple(mul_xi(c1)), dbl(a.c[1]));
+    r.c[4] = sub(triple(c0), dbl(a.c[4]));
+    r.c[2] = sub(triple(b0), dbl(a.c[2]));
+    r.c[5] = add(triple(b1), dbl(a.c[5]));
+    return r;
+}
+// a^x for a in the cyclotomic subgroup
 Fq12 f12_exp_x(const Fq12& a) {
+    static const int mode = getenv("ZKR_PAIRING_CYC") ? atoi(getenv("ZKR_PAIRING_CYC")) : 1;   // 0: generic squarings, 2: self-check
     Fq12 r = a;
     for (int i = 61; i >= 0; i--) {       // kBnX has 63 bits, top bit consumed by r = a
-        r = f12_sqr(r);
+        if (mode == 2) {
+            const Fq12 g = f12_sqr(r), c = f12_cyc_sqr(r);
+            for (int k = 0; k < 6; k++)
+                if (!eq(g.c[k], c.c[k])) {
+                    fprintf(stderr, "zkr: cyclotomic squaring self-check FAILED\n");
+                    abort();
+                }
+            r = c;
+        } else {
+            r = mode ? f12_cyc_sqr(r) : f12_sqr(r);
+        }
         if ((kBnX >> i) & 1) r = f12_mul(r, a);
     }
     return r;
@@ -464,8 +542,96 @@ bool line_step(Fq12& f, MillerState* st, int n, bool doubling, const Fq2* sx, co
     return true;
 }
 
+// ---- the same loop in homogeneous projective coordinates: no inversion at all (the affine loop above pays one Fq
+// inversion = ~380 multiplications per line step, which is most of its time for a 4-pair product).
+// Formulas of Costello, Lange, Naehrig, "Faster pairing computations on curves with high-degree twists" (D-type twist
+// y^2 = x^3 + b'), lines scaled by an element of Fq2:
+//   doubling   T = (X, Y, Z):  l = -2YZ yP + 3X^2 xP w + (3b'Z^2 - Y^2) w^3
+//   addition   T + Q, Q affine: theta = Y - yQ Z, lambda = X - xQ Z:  l = lambda yP - theta xP w + (theta xQ - lambda yQ) w^3
+// (the affine lines yP - lam xP w + (lam x1 - y1) w^3 times -2YZ, resp. times lambda).
+struct ProjState {
+    Fq2 x, y, z;       // running twist point T
+    Fq2 qx, qy;        // Q
+    Fq px, py;         // P
+};
+inline Fq half(const Fq& a) {                 // a / 2 mod p
+    static const Fq kHalf = inv(add(kOne, kOne));
+    return mul(a, kHalf);
+}
+inline Fq2 half(const Fq2& a) { return {half(a.c0), half(a.c1)}; }
+inline void proj_double_step(Fq12& f, ProjState& s) {
+    const Fq2 bt = fq2_from_u64(kTwistB);
+    Fq2 a = half(mul(s.x, s.y));
+    Fq2 b = sqr(s.y), c = sqr(s.z);
+    Fq2 e = mul(bt, add(dbl(c), c));
+    Fq2 ff = add(dbl(e), e);
+    Fq2 g = half(add(b, ff));
+    Fq2 h = sub(sqr(add(s.y, s.z)), add(b, c));
+    Fq2 i = sub(e, b);
+    Fq2 j = sqr(s.x);
+    Fq2 e2 = sqr(e);
+    s.x = mul(a, sub(b, ff));
+    s.y = sub(sqr(g), add(dbl(e2), e2));
+    s.z = mul(b, h);
+    f = f12_mul_line2(f, neg(mul_fq(h, s.py)), mul_fq(add(dbl(j), j), s.px), i);
+}
+// false: T == +-S (cannot happen for points of order r inside the loop)
+inline bool proj_add_step(Fq12& f, ProjState& s, const Fq2& sx, const Fq2& sy) {
+    Fq2 theta = sub(s.y, mul(sy, s.z));
+    Fq2 lambda = sub(s.x, mul(sx, s.z));
+    if (is_zero(lambda)) return false;
+    Fq2 c = sqr(theta), d = sqr(lambda);
+    Fq2 e = mul(lambda, d), ff = mul(s.z, c), g = mul(s.x, d);
+    Fq2 h = sub(add(e, ff), dbl(g));
+    Fq2 y3 = sub(mul(theta, sub(g, h)), mul(e, s.y));
+    s.x = mul(lambda, h);
+    s.y = y3;
+    s.z = mul(s.z, e);
+    Fq2 j = sub(mul(theta, sx), mul(lambda, sy));
+    f = f12_mul_line2(f, mul_fq(lambda, s.py), neg(mul_fq(theta, s.px)), j);
+    return true;
+}
+bool miller_product_projective(const G1A* P, const G2A* Q, int n_in, Fq12* out) {
+    ProjState st[8];
+    int n = 0;
+    for (int i = 0; i < n_in; i++) {
+        if (P[i].inf || Q[i].inf) continue;       // e(O, Q) = e(P, O) = 1
+        st[n++] = {Q[i].x, Q[i].y, kOne2, Q[i].x, Q[i].y, P[i].x, P[i].y};
+    }
+    Fq12 f = f12_one();
+    if (n) {
+        for (int b = 63; b >= 0; b--) {           // bits below the leading one of the 65-bit loop count
+            f = f12_sqr(f);
+            for (int i = 0; i < n; i++) {
+                if (is_zero(st[i].y)) return false;
+                proj_double_step(f, st[i]);
+            }
+            if ((kAteLoop >> b) & 1)
+                for (int i = 0; i < n; i++)
+                    if (!proj_add_step(f, st[i], st[i].qx, st[i].qy)) return false;
+        }
+        // Q1 = pi(Q), -Q2 = -pi^2(Q) on the twist
+        const Fq2 g12 = gamma(1, 2), g13 = gamma(1, 3), g22 = gamma(2, 2), g23 = gamma(2, 3);
+        for (int i = 0; i < n; i++) {
+            if (!proj_add_step(f, st[i], mul(conj(st[i].qx), g12), mul(conj(st[i].qy), g13))) return false;
+            if (!proj_add_step(f, st[i], mul(st[i].qx, g22), neg(mul(st[i].qy, g23)))) return false;
+        }
+    }
+    *out = f;
+    return true;
+}
+
 // prod_i e(P_i, Q_i) == 1 ?   ok=false: a degenerate line was hit (inputs outside the prime-order groups)
+bool pairing_product_is_one_affine(const G1A* P, const G2A* Q, int n_in, bool* ok);
 bool pairing_product_is_one(const G1A* P, const G2A* Q, int n_in, bool* ok) {
+    static const bool use_affine = getenv("ZKR_PAIRING_AFFINE") && atoi(getenv("ZKR_PAIRING_AFFINE"));   // cross-check knob
+    if (use_affine) return pairing_product_is_one_affine(P, Q, n_in, ok);
+    Fq12 f;
+    *ok = miller_product_projective(P, Q, n_in, &f);
+    if (!*ok) return false;
+    return f12_is_one(final_exp(f));
+}
+bool pairing_product_is_one_affine(const G1A* P, const G2A* Q, int n_in, bool* ok) {
     MillerState st[8];
     int n = 0;
     for (int i = 0; i < n_in; i++) {

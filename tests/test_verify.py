@@ -121,6 +121,49 @@ def test_pairing_check_agrees_with_the_oracle_on_random_products():
         assert pairing_check(pairs) == (0, int(want))
 
 
+def test_pairing_variants_agree():
+    """The default host pairing (projective Miller loop, complex / cyclotomic squarings) against the first
+    implementation (affine loop with batched inversions, generic squarings: ZKR_PAIRING_AFFINE=1 ZKR_PAIRING_CYC=0) and
+    against itself with the cyclotomic-squaring self-check on (ZKR_PAIRING_CYC=2 aborts on a mismatch).  The knobs are
+    read once per process, so the variants run in child processes on the same byte strings."""
+    import os
+    import subprocess
+    import sys
+    rng = random.Random(17)
+    cases = []
+    for trial in range(8):
+        n = 1 + trial % 4
+        ks = [rng.randrange(1, R) for _ in range(n)]
+        ls = [rng.randrange(1, R) for _ in range(n)]
+        pairs = [(bn.G1.mul(bn.G1_GEN, k), bn.G2.mul(bn.G2_GEN, l)) for k, l in zip(ks, ls)]
+        tot = sum(k * l for k, l in zip(ks, ls)) % R
+        if trial % 3 == 1:
+            tot = (tot + 1) % R                                # product != 1
+        pairs.append((bn.G1.neg(bn.G1.mul(bn.G1_GEN, tot)), bn.G2_GEN))
+        if trial == 5:
+            pairs.insert(1, (None, bn.G2_GEN))                 # infinity contributes 1
+        cases.append((pairs, trial % 3 != 1))
+    blobs = [(b"".join(_b1(p) for p, _ in pairs).hex(), b"".join(_b2(q) for _, q in pairs).hex(), len(pairs)) for pairs, _ in cases]
+    here = [pairing_check(pairs) for pairs, _ in cases]
+    assert here == [(0, int(w)) for _, w in cases]
+    child = ("import sys, json, ctypes as C\n"
+             "sys.path.insert(0, %r)\n"
+             "from simple_zk_rollups_b200 import _lib\n"
+             "L = _lib.lib()\n"
+             "out = []\n"
+             "for g1, g2, n in json.loads(sys.stdin.read()):\n"
+             "    ok = C.c_int(-1)\n"
+             "    rc = L.zkr_pairing_check(bytes.fromhex(g1), bytes.fromhex(g2), n, C.byref(ok))\n"
+             "    out.append([rc, ok.value])\n"
+             "print(json.dumps(out))\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for env in ({"ZKR_PAIRING_AFFINE": "1", "ZKR_PAIRING_CYC": "0"}, {"ZKR_PAIRING_CYC": "2"}, {"ZKR_PAIRING_AFFINE": "1"}):
+        e = dict(os.environ)
+        e.update(env)
+        r = subprocess.run([sys.executable, "-c", child], input=json.dumps(blobs), capture_output=True, text=True, env=e, timeout=300)
+        assert r.returncode == 0, r.stderr[-500:]
+        assert [tuple(x) for x in json.loads(r.stdout.strip().splitlines()[-1])] == here, env
+
+
 def test_pairing_check_rejects_invalid_points():
     G1, G2 = bn.G1_GEN, bn.G2_GEN
     assert pairing_check([((1, 3), G2)])[0] == -1                       # not on the G1 curve
