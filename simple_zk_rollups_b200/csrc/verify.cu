@@ -308,8 +308,8 @@ Fq12 f12_mul_line(const Fq12& a, const Fq& l0, const Fq2& l1, const Fq2& l3) {
     return r;
 }
 // a * (l0 + l1 w + l3 w^3), l0 in Fq2 (projective Miller loop: the line is scaled by an Fq2 factor, which the
-// final exponentiation removes)
-Fq12 f12_mul_line2(const Fq12& a, const Fq2& l0, const Fq2& l1, const Fq2& l3) {
+// final exponentiation removes).  Schoolbook version: 18 Fq2 multiplications; kept as the self-check reference.
+Fq12 f12_mul_line2_ref(const Fq12& a, const Fq2& l0, const Fq2& l1, const Fq2& l3) {
     Fq2 t[9];
     for (int i = 0; i < 9; i++) t[i] = kZero2;
     for (int i = 0; i < 6; i++) {
@@ -319,6 +319,39 @@ Fq12 f12_mul_line2(const Fq12& a, const Fq2& l0, const Fq2& l1, const Fq2& l3) {
     }
     Fq12 r;
     for (int k = 0; k < 6; k++) r.c[k] = k < 3 ? add(t[k], mul_xi(t[k + 6])) : t[k];
+    return r;
+}
+// (a0 + a1 v + a2 v^2)(x0 + x1 v) in Fq2[v]/(v^3 - xi): 5 Fq2 multiplications
+inline void f6_mul_by_01(const Fq2* a, const Fq2& x0, const Fq2& x1, Fq2* r) {
+    const Fq2 t0 = mul(a[0], x0), t1 = mul(a[1], x1);
+    r[1] = sub(sub(mul(add(a[0], a[1]), add(x0, x1)), t0), t1);
+    r[0] = add(t0, mul_xi(mul(a[2], x1)));
+    r[2] = add(t1, mul(a[2], x0));
+}
+// Same product over the tower (v = w^2): a = E + O w, line = L0 + L1 w with L0 = l0, L1 = l1 + l3 v;
+//   a * line = (E L0 + v O L1) + ((E + O)(L0 + L1) - E L0 - O L1) w :  3 + 5 + 5 = 13 Fq2 multiplications.
+Fq12 f12_mul_line2(const Fq12& a, const Fq2& l0, const Fq2& l1, const Fq2& l3) {
+    const Fq2 E[3] = {a.c[0], a.c[2], a.c[4]}, O[3] = {a.c[1], a.c[3], a.c[5]};
+    const Fq2 S[3] = {add(E[0], O[0]), add(E[1], O[1]), add(E[2], O[2])};
+    Fq2 t0[3], t1[3], t2[3];
+    for (int i = 0; i < 3; i++) t0[i] = mul(E[i], l0);
+    f6_mul_by_01(O, l1, l3, t1);
+    f6_mul_by_01(S, add(l0, l1), l3, t2);
+    const Fq2 vt1[3] = {mul_xi(t1[2]), t1[0], t1[1]};
+    Fq12 r;
+    for (int i = 0; i < 3; i++) {
+        r.c[2 * i] = add(t0[i], vt1[i]);
+        r.c[2 * i + 1] = sub(sub(t2[i], t0[i]), t1[i]);
+    }
+    static const bool self_check = getenv("ZKR_PAIRING_CYC") && atoi(getenv("ZKR_PAIRING_CYC")) == 2;
+    if (self_check) {
+        const Fq12 g = f12_mul_line2_ref(a, l0, l1, l3);
+        for (int k = 0; k < 6; k++)
+            if (!eq(g.c[k], r.c[k])) {
+                fprintf(stderr, "zkr: sparse line product self-check FAILED\n");
+                abort();
+            }
+    }
     return r;
 }
 inline Fq12 f12_conj(const Fq12& a) {       // the q^6 Frobenius: w -> -w
