@@ -1,5 +1,6 @@
 """GPU parity: bucketed MSM (G1 and G2) vs the oracle's per-point double-and-add, bit-exact."""
 import ctypes as C
+import os
 import random
 
 import numpy as np
@@ -97,3 +98,15 @@ def test_msm_arithmetic_progression(zctx, group, n):
         exp = fb.mul_many([e])[0]
         assert msm(zctx, group, h, sc) == exp, name
     L.zkr_bases_free(h)
+
+
+@pytest.mark.skipif(not os.environ.get("ZKR_RUN_EXPERIMENTS"), reason="default-off experiment (ZKR_G2_SMEM_ACC); run with ZKR_RUN_EXPERIMENTS=1")
+@pytest.mark.parametrize("n,c", [(1, 0), (41, 4), (200, 0), (200, 11), (1500, 0)])
+def test_g2_smem_accumulator_experiment(zctx, n, c):
+    """k_accum_affine_smz (accumulator ZZ / ZZZ in shared memory, 168 registers) must give the bytes of the default
+    G2 path on every scalar set, duplicates / opposites / infinities included."""
+    os.environ["ZKR_G2_SMEM_ACC"] = "1"
+    try:
+        test_msm_small(zctx, 2, n, c)
+    finally:
+        del os.environ["ZKR_G2_SMEM_ACC"]

@@ -19,4 +19,16 @@ ncu -i gpurun_out/r02a_ntt.ncu-rep --page raw --csv > gpurun_out/r02a_ntt_raw.cs
 ncu -i gpurun_out/r02a_ntt.ncu-rep --page source --csv --print-source sass > gpurun_out/r02a_ntt_source.csv 2>/dev/null
 python tools/ncu_source_top.py gpurun_out/r02a_ntt_source.csv --top 25 > gpurun_out/r02a_ntt_source_top.txt 2>&1
 gzip -9 -f gpurun_out/r02a_ntt_source.csv; rm -f gpurun_out/r02a_ntt.ncu-rep
+echo "== experiment: G2 accumulation with ZZ / ZZZ in shared memory (168 registers, 3 CTAs/SM): parity, then A/B"
+ZKR_RUN_EXPERIMENTS=1 timeout 300 python -m pytest tests/test_gpu_msm.py -m gpu -x -q -k smem_accumulator 2>&1 | tail -3
+timeout 200 python bench.py --no-cpu --steps 10 > gpurun_out/r02a_bench_default.json 2>/dev/null
+ZKR_G2_SMEM_ACC=1 timeout 200 python bench.py --no-cpu --steps 10 > gpurun_out/r02a_bench_g2smz.json 2>/dev/null
+python - <<PY
+import json
+for f in ("gpurun_out/r02a_bench_default.json", "gpurun_out/r02a_bench_g2smz.json"):
+    try:
+        d = json.loads(open(f).read().strip().splitlines()[-1]); print(f, d["ms_per_step"], d["prove_ms_serial"], d["stage_ms_overlapped"]["msm_b2_ms"])
+    except Exception as e:
+        print(f, "failed", e)
+PY
 du -sm gpurun_out
