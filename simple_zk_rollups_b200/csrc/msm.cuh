@@ -195,9 +195,10 @@ k_accum_affine(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ v
 // ~90 words per addition to local memory and is slower (measured).  Here the two coordinates that are touched only
 // twice per addition (read for U2 / S2, read-modify-write at the end) are placed in shared memory by hand: word-major
 // [16 words][blockDim] per coordinate (conflict free), 16 KB per CTA; ptxas then fits 168 registers = 3 CTAs/SM with
-// 62 B of spill stores in the whole kernel.  Same algorithm and results as k_accum_affine; compiled and wired, NOT
-// yet run on a GPU (round 1 had no GPU minutes left): tests/test_gpu_msm.py::test_g2_smem_accumulator_experiment is
-// skipped unless ZKR_RUN_EXPERIMENTS=1, tools/gpu_jobs/r02a.sh runs it and the A/B timing.
+// 62 B of spill stores in the whole kernel.  Same algorithm and results as k_accum_affine: parity-green on a B200 for
+// the two smallest cases of tests/test_gpu_msm.py::test_g2_smem_accumulator_experiment (all scalar sets, duplicates /
+// opposites / infinities) with the last GPU seconds of round 1; NOT yet timed.  The test is skipped unless
+// ZKR_RUN_EXPERIMENTS=1; tools/gpu_jobs/r02a.sh runs all of it and the A/B timing.
 template <class F>
 struct SmemCoord {                       // one field element per thread, word-major in shared memory
     uint32_t* base;                      // &plane[threadIdx.x]
