@@ -82,8 +82,9 @@ int zkr_ctx_synchronize(zkr_ctx* ctx);
 uint64_t zkr_ctx_kernel_launches(const zkr_ctx* ctx);
 
 /* Per-kernel device timing (CUDA events on the launching stream) for roofline reporting.
- * id: 0 = G1 bucket accumulation (k_accum_affine<Fq>), 1 = G2 bucket accumulation, 2 = NTT pass.
- * units: work summed over the recorded launches -- mixed additions for ids 0/1, elements for id 2. */
+ * id: 0 = G1 bucket accumulation (k_accum_affine<Fq>), 1 = G2 bucket accumulation, 2 = NTT pass (local),
+ *     3 = the NTT pass of a sharded transform whose write-back is the all-to-all (remote stores).
+ * units: work summed over the recorded launches -- mixed additions for ids 0/1, elements for ids 2/3. */
 int zkr_ctx_set_profile(zkr_ctx* ctx, int on);
 /* on != 0: zkr_prove runs its stages back to back on the ctx stream instead of forking five streams
  * (isolated per-kernel timings; the default overlaps the MSMs and the H pipeline). */
@@ -125,8 +126,11 @@ int zkr_pkey_load_json(zkr_ctx* ctx, const char* json, size_t len, zkr_pkey** ou
 
 /* ---- prove -------------------------------------------------------------------------- */
 /* witness: n_signals x 32 B std form (binarifyWitness layout), HOST memory.
- * r32 / s32: blinding scalars, 32 B std form < r, or NULL for 0 (the snarkjs debug mode;
- *   production callers pass CSPRNG output -- websnark draws them internally).
+ * r32 / s32: blinding scalars, 32 B std form < r.  NULL = the library draws the scalar uniformly from
+ *   [0, r) with the OS CSPRNG (getrandom), as websnark's groth16GenProof does internally: a caller who
+ *   passes nothing gets a zero-knowledge proof.  The snarkjs debug mode (r = s = 0: deterministic, NOT
+ *   zero-knowledge) and fixed-(r, s) parity runs pass explicit buffers.  The sharded prove needs the same
+ *   (r, s) on every rank and therefore rejects NULL.
  * out_proof: 256 B = pi_a (x|y) | pi_b (x.c0|x.c1|y.c0|y.c1) | pi_c (x|y), std form, affine,
  *   i.e. exactly the integers websnark prints as decimal strings (z omitted: "1" / ["1","0"]).
  *   A point at infinity is encoded as all-zero coordinates. */
@@ -134,14 +138,20 @@ int zkr_prove(zkr_ctx* ctx, const zkr_pkey* pk, const void* witness, size_t n_si
               const void* r32, const void* s32, void* out_proof, zkr_stats* stats);
 /* Same with the witness already resident in device memory of ctx's GPU (d_witness) and the
  * proof written to device memory (d_out_proof, 256 B); asynchronous w.r.t. the host, ordered
- * on the ctx stream (zkr_ctx_set_stream). */
+ * on the ctx stream (zkr_ctx_set_stream).  Being asynchronous it cannot return
+ * ZKR_E_WITNESS_RANGE: invalid inputs (a value >= r, witness[0] != 1) give a meaningless proof and
+ * set device-side flags that stay set until zkr_prove_check reads them.  zkr_prove and
+ * zkr_prove_batch start from clean flags and report on their own inputs only. */
 int zkr_prove_dev(zkr_ctx* ctx, const zkr_pkey* pk, const void* d_witness, size_t n_signals,
                   const void* r32, const void* s32, void* d_out_proof);
+/* Synchronise the ctx stream, then report and clear the input-validity flags of every zkr_prove_dev
+ * on `pk` since the last check: ZKR_OK or ZKR_E_WITNESS_RANGE. */
+int zkr_prove_check(zkr_ctx* ctx, const zkr_pkey* pk);
 /* n_proofs independent proofs over n_ctx contexts (one per GPU; pks[i] is the same key loaded on
  * ctxs[i]'s device), scheduled round-robin, one in flight per GPU.  witnesses: n_proofs buffers. */
 int zkr_prove_batch(zkr_ctx* const* ctxs, const zkr_pkey* const* pks, int n_ctx,
                     const void* const* witnesses, size_t n_signals, int n_proofs,
-                    const void* rs32 /* n_proofs x 64 B (r|s) or NULL */, void* out_proofs);
+                    const void* rs32 /* n_proofs x 64 B (r|s), or NULL = fresh CSPRNG pairs */, void* out_proofs);
 
 /* ---- verify -------------------------------------------------- */
 /* Replaces snarkjs groth.isValid(verifyingKey, proof, publicSignals) at
@@ -206,6 +216,14 @@ int zkr_ntt(zkr_ctx* ctx, void* data, int log_n, int mode, int on_device);
  * (2^log_m x 32 B std form, device memory, clobbered); h_out receives h_0..h_{m-1} std form in
  * BIT-REVERSED order when bitrev_out != 0 (what the prover feeds to the hExps MSM) or natural order. */
 int zkr_h_from_evals_dev(zkr_ctx* ctx, void* d_a_t, void* d_b_t, int log_m, void* d_h_out, int bitrev_out);
+/* Workload generator for the NTT sweeps (BASELINE.json configs[3]): d_out[p] = c * g^j(p), std form, device
+ * memory; c32, g32: 32 B std form, host.  world == 1: j(p) = start + p.  world = 2, 4, 8: d_out is `rank`'s
+ * COLS slab (n_local = 2^log_n / world elements) of a zkr_ntt_sharded transform of 2^log_n elements, j(p)
+ * the element's index in the whole vector (start ignored).  A dense vector whose transform the host can
+ * check in closed form at any size: X[k] = sum_j c g^j w^(jk) = c (g^N - 1) / (g w^k - 1).
+ * Asynchronous, ordered on the ctx stream. */
+int zkr_fill_geometric(zkr_ctx* ctx, void* d_out, size_t n_local, const void* c32, const void* g32,
+                       uint64_t start, int log_n, int world, int rank);
 
 /* ---- multi-GPU: peer-memory communicator, sharded MSM, sharded four-step NTT ----------------
  * One zkr_comm per rank (GPU).  Each rank owns a device slab (flags | gather slots | two exchange
@@ -223,7 +241,11 @@ int zkr_comm_export(const zkr_comm* c, void* handle64);
 int zkr_comm_connect(zkr_comm* c, const void* handles /* world x 64 B, rank order */);
 int zkr_comm_connect_local(zkr_comm* const* comms, int world);
 /* device-side flag barrier across the ranks, ordered on the ctx stream (bounded spin: a missing peer
- * turns into ZKR_E_NCCL at the next zkr_comm_check / synchronising call, not a hang) */
+ * turns into ZKR_E_NCCL at the next zkr_comm_check / synchronising call, not a hang).  Every collective
+ * entry point validates its arguments on the host BEFORE it launches a barrier, so a rank that returns
+ * ZKR_E_INVALID has not half-entered a collective; if a barrier does time out (a peer died or bailed out
+ * on a CUDA error) the ranks' barrier epochs may differ, the communicator is marked dead -- every later
+ * call on it returns ZKR_E_NCCL -- and it must be destroyed and re-created on every rank. */
 int zkr_comm_barrier(zkr_comm* c);
 int zkr_comm_check(zkr_comm* c);
 /* device pointer of this rank's exchange buffer 0 / 1 */

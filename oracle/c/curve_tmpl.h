@@ -87,6 +87,29 @@ static void NAME(to_affine)(NAME(aff)* r, const NAME(jac)* p) {
     F_MUL(&r->x, &p->x, &zi2); F_MUL(&r->y, &p->y, &zi3); r->inf = 0;
 }
 
+/* out[i] = base + i * step (affine, i < n): a chain of mixed additions, then ONE shared inversion for the n
+ * conversions to affine (Montgomery's trick).  Host-side workload generator for the arithmetic-progression MSM
+ * check of SURVEY.md 8(d) config 3 (tests only). */
+static void NAME(ap_points)(NAME(aff)* out, const NAME(aff)* base, const NAME(aff)* step, size_t n) {
+    if (n == 0) return;
+    NAME(jac)* j = (NAME(jac)*)malloc(sizeof(NAME(jac)) * n);
+    F_T* pre = (F_T*)malloc(sizeof(F_T) * n);
+    j[0].x = base->x; j[0].y = base->y; F_SET_ONE(&j[0].z);
+    if (base->inf) NAME(jset_inf)(&j[0]);
+    for (size_t i = 1; i < n; i++) NAME(jmadd)(&j[i], &j[i - 1], step);
+    F_T acc; F_SET_ONE(&acc);
+    for (size_t i = 0; i < n; i++) { pre[i] = acc; if (!NAME(jis_inf)(&j[i])) F_MUL(&acc, &acc, &j[i].z); }
+    F_T inv; F_INV(&inv, &acc);
+    for (size_t i = n; i-- > 0;) {
+        if (NAME(jis_inf)(&j[i])) { out[i].inf = 1; F_SET_ZERO(&out[i].x); F_SET_ZERO(&out[i].y); continue; }
+        F_T zi, zi2, zi3;
+        F_MUL(&zi, &inv, &pre[i]); F_MUL(&inv, &inv, &j[i].z);
+        F_SQR(&zi2, &zi); F_MUL(&zi3, &zi2, &zi);
+        F_MUL(&out[i].x, &j[i].x, &zi2); F_MUL(&out[i].y, &j[i].y, &zi3); out[i].inf = 0;
+    }
+    free(pre); free(j);
+}
+
 /* ---- multi-scalar multiplication -------------------------------------------------------------
  * mode 0: the snarkjs genProof structure -- one double-and-add per point, summed (prover_groth.js).
  * mode 1: Pippenger buckets with unsigned c-bit windows; windows are spread over `threads`

@@ -429,6 +429,118 @@ int oracle_prove(const uint8_t* pk, size_t pk_len, const uint8_t* witness, size_
     return 0;
 }
 
+/* out[i] = base + i * step, affine Fq-M bytes (64 B G1 / 128 B G2; infinity = zeros); base, step affine Fq-M.
+ * With base = a0 G and step = d G this is P_i = (a0 + i d) G of SURVEY.md 8(d) config 3, made on the host. */
+int oracle_ap_points(int group, const uint8_t* base, const uint8_t* step, size_t n, uint8_t* out) {
+    if (group == 1) {
+        g1_aff b, s, *o = (g1_aff*)malloc(sizeof(g1_aff) * (n ? n : 1));
+        load_g1(&b, base, 1); load_g1(&s, step, 1);
+        g1_ap_points(o, &b, &s, n);
+        for (size_t i = 0; i < n; i++) {
+            if (o[i].inf) { memset(out + 64 * i, 0, 64); continue; }
+            memcpy(out + 64 * i, o[i].x.v, 32); memcpy(out + 64 * i + 32, o[i].y.v, 32);
+        }
+        free(o);
+    } else {
+        g2_aff b, s, *o = (g2_aff*)malloc(sizeof(g2_aff) * (n ? n : 1));
+        load_g2(&b, base, 1); load_g2(&s, step, 1);
+        g2_ap_points(o, &b, &s, n);
+        for (size_t i = 0; i < n; i++) {
+            if (o[i].inf) { memset(out + 128 * i, 0, 128); continue; }
+            memcpy(out + 128 * i, o[i].x.c0.v, 32); memcpy(out + 128 * i + 32, o[i].x.c1.v, 32);
+            memcpy(out + 128 * i + 64, o[i].y.c0.v, 32); memcpy(out + 128 * i + 96, o[i].y.c1.v, 32);
+        }
+        free(o);
+    }
+    return 0;
+}
+
+/* Toxic-waste exponent sums (oracle/groth16.py exponent_check_flat, restated): for one sparse matrix given as
+ * (sig, row, cid) triplets with coefficients pool[cid],
+ *     tot  = sum_e w[sig_e] pool[cid_e] L_{row_e}(tau),     priv = the same over entries with sig_e > n_public,
+ * L_c(tau) = omega^c (tau^m - 1) / (m (tau - omega^c)) on the domain <omega_m> (lagrange_at).  No MSM / NTT code.
+ * w: n x 32 B, pool: n_pool x 32 B, tau32, out: standard form.  One shared inversion (Montgomery's trick). */
+int oracle_exponent_sums(int log_m, const uint8_t* tau32, const uint8_t* w, const uint8_t* pool, size_t n_pool,
+                         const uint32_t* sig, const uint32_t* row, const uint32_t* cid, size_t nnz, uint32_t n_public,
+                         uint8_t* tot32, uint8_t* priv32) {
+    const size_t m = (size_t)1 << log_m;
+    fe tau, om = fr_root(log_m), zt, k, minv, t;
+    rd_fe(&tau, tau32); fe_to_mont(&tau, &tau, &FR);
+    zt = tau;
+    for (int i = 0; i < log_m; i++) fe_sqr(&zt, &zt, &FR);
+    fe_sub(&zt, &zt, &FR.one, &FR);
+    fe mm = {{(uint64_t)m, 0, 0, 0}};
+    fe_to_mont(&mm, &mm, &FR); fe_inv(&minv, &mm, &FR);
+    fe_mul(&k, &zt, &minv, &FR);
+    fe* lag = (fe*)malloc(sizeof(fe) * m);        /* tau - omega^c, then L_c(tau), Montgomery */
+    fe* pre = (fe*)malloc(sizeof(fe) * m);
+    fe* wc = (fe*)malloc(sizeof(fe) * m);
+    fe cur = FR.one, acc = FR.one;
+    for (size_t c = 0; c < m; c++) {
+        wc[c] = cur;
+        fe_sub(&lag[c], &tau, &cur, &FR);
+        pre[c] = acc;
+        fe_mul(&acc, &acc, &lag[c], &FR);
+        fe_mul(&cur, &cur, &om, &FR);
+    }
+    fe inv; fe_inv(&inv, &acc, &FR);
+    for (size_t c = m; c-- > 0;) {
+        fe di; fe_mul(&di, &inv, &pre[c], &FR);
+        fe_mul(&inv, &inv, &lag[c], &FR);
+        fe_mul(&t, &k, &wc[c], &FR);
+        fe_mul(&lag[c], &t, &di, &FR);
+    }
+    fe* pm = (fe*)malloc(sizeof(fe) * (n_pool ? n_pool : 1));
+    for (size_t i = 0; i < n_pool; i++) { rd_fe(&pm[i], pool + 32 * i); fe_to_mont(&pm[i], &pm[i], &FR); }
+    fe tot = {{0, 0, 0, 0}}, priv = {{0, 0, 0, 0}};
+    for (size_t e = 0; e < nnz; e++) {
+        fe ws; rd_fe(&ws, w + 32 * (size_t)sig[e]);
+        fe_mul(&t, &ws, &pm[cid[e]], &FR);        /* standard x Montgomery -> standard */
+        fe_mul(&t, &t, &lag[row[e]], &FR);
+        fe_add(&tot, &tot, &t, &FR);
+        if (sig[e] > n_public) fe_add(&priv, &priv, &t, &FR);
+    }
+    memcpy(tot32, tot.v, 32); memcpy(priv32, priv.v, 32);
+    free(pm); free(wc); free(pre); free(lag);
+    return 0;
+}
+
+/* Horner evaluation over Fr: out = sum_j coeffs[j] x^j; coeffs n x 32 B, x, out 32 B, all standard form.
+ * The NTT check of SURVEY.md 8(d) config 4 ("Horner evaluation at 8 random points vs. transformed values"). */
+int oracle_horner(const uint8_t* coeffs, size_t n, const uint8_t* x32, uint8_t* out32) {
+    fe x, acc = {{0, 0, 0, 0}}, c;
+    rd_fe(&x, x32); fe_to_mont(&x, &x, &FR);
+    for (size_t j = n; j-- > 0;) {
+        fe_mul(&acc, &acc, &x, &FR);          /* standard-form acc times Montgomery x stays standard form */
+        rd_fe(&c, coeffs + 32 * j);
+        fe_add(&acc, &acc, &c, &FR);
+    }
+    memcpy(out32, acc.v, 32);
+    return 0;
+}
+
+/* affine point addition / scalar multiplication (k: 32 B standard form), points Fq-M affine bytes, infinity = zeros:
+ * the operations of the alt_bn128 ecAdd / ecMul precompiles TxVerifier.sol:59-88 calls (EIP-196 known answers) */
+int oracle_g1_add(const uint8_t* p, const uint8_t* q, uint8_t* out) {
+    g1_aff a, b; load_g1(&a, p, 1); load_g1(&b, q, 1);
+    g1_jac j; j.x = a.x; j.y = a.y; j.z = FQ.one; if (a.inf) g1_jset_inf(&j);
+    g1_jmadd(&j, &j, &b);
+    g1_aff r; g1_to_affine(&r, &j);
+    if (r.inf) { memset(out, 0, 64); return 0; }
+    memcpy(out, r.x.v, 32); memcpy(out + 32, r.y.v, 32);
+    return 0;
+}
+int oracle_g1_mul(const uint8_t* p, const uint8_t* k32, uint8_t* out) {
+    g1_aff a; load_g1(&a, p, 1);
+    uint64_t k[4]; memcpy(k, k32, 32);
+    g1_jac j, r; j.x = a.x; j.y = a.y; j.z = FQ.one; if (a.inf) g1_jset_inf(&j);
+    g1_jmul(&r, &j, k);
+    g1_aff o; g1_to_affine(&o, &r);
+    if (o.inf) { memset(out, 0, 64); return 0; }
+    memcpy(out, o.x.v, 32); memcpy(out + 32, o.y.v, 32);
+    return 0;
+}
+
 /* element-wise Montgomery product in Fq (field = 0) or Fr (field = 1): KAT hook for the tests */
 int oracle_field_mul(int field, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
     const field_t* F = field ? &FR : &FQ;

@@ -333,10 +333,10 @@ def exponent_check(pk, secrets, witness, proof, r=0, s=0):
             and proof["pi_c"] == f1.mul_many([c])[0])
 
 
-def exponent_check_flat(mats, pool, n_public, witness, toxic, m, proof, r=0, s=0):
-    """exponent_check for large synthetic circuits: one pass over the sparse entries, no per-signal
-    tables.  mats = {"A": (sig, row, cid)} WITH the input-consistency rows in A; pool = coefficient ints."""
-    tau, alpha, beta, gamma, delta = [x % R for x in toxic]
+def exponent_sums_flat(mats, pool, n_public, witness, toxic, m):
+    """The sparse pass of exponent_check_flat: per matrix, tot = sum over entries of w[sig] coeff L_row(tau) and
+    priv = the same over the private signals.  Independent of (r, s): compute once, check several proofs."""
+    tau = toxic[0] % R
     lag = lagrange_at(m, tau)
     w = [x % R for x in witness]
     tot, priv = {}, {}
@@ -348,6 +348,16 @@ def exponent_check_flat(mats, pool, n_public, witness, toxic, m, proof, r=0, s=0
             if sg > n_public:
                 p += v
         tot[name], priv[name] = t % R, p % R
+    return tot, priv
+
+
+def exponent_check_flat(mats, pool, n_public, witness, toxic, m, proof, r=0, s=0, sums=None):
+    """exponent_check for large synthetic circuits: one pass over the sparse entries, no per-signal
+    tables.  mats = {"A": (sig, row, cid)} WITH the input-consistency rows in A; pool = coefficient ints.
+    sums = (tot, priv) from exponent_sums_flat, or from its C restatement oracle.cbind.exponent_sums (2^22-sized
+    circuits; tests/test_oracle_c.py holds the two equal)."""
+    tau, alpha, beta, gamma, delta = [x % R for x in toxic]
+    tot, priv = sums if sums is not None else exponent_sums_flat(mats, pool, n_public, witness, toxic, m)
     a = (alpha + tot["A"] + r * delta) % R
     b = (beta + tot["B"] + s * delta) % R
     kpriv = (beta * priv["A"] + alpha * priv["B"] + priv["C"]) % R

@@ -66,6 +66,9 @@ _SIGS = {
                             C.c_void_p, C.POINTER(Stats)]),
     "zkr_prove_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
                                 C.c_void_p]),
+    "zkr_prove_check": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "zkr_fill_geometric": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int,
+                                     C.c_int, C.c_int]),
     "zkr_prove_batch": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int,
                                   C.POINTER(C.c_void_p), C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]),
     "zkr_bases_load": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]),

@@ -99,7 +99,16 @@ int comm_check(zkr_comm* c, cudaStream_t st) {
     ZKR_CUDA(cudaMemcpyAsync(&e, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
     ZKR_CUDA(cudaStreamSynchronize(st));
     if (e) {
-        set_error("rank %d: a peer did not reach the barrier within 20 s", c->rank);
+        // report once, then clear (like the witness range flags): the flag says "a barrier since the last check timed
+        // out".  The ranks' barrier epochs may have diverged at that point -- a rank that bailed out never launched its
+        // barrier -- so the communicator must be destroyed and re-created on EVERY rank before it is used again.
+        ZKR_CUDA(cudaMemsetAsync(c->d_err, 0, sizeof(int), st));
+        c->dead = true;
+        set_error("rank %d: a peer did not reach the barrier within 20 s; destroy and re-create the communicator on every rank", c->rank);
+        return ZKR_E_NCCL;
+    }
+    if (c->dead) {
+        set_error("rank %d: this communicator saw a barrier timeout earlier; destroy and re-create it on every rank", c->rank);
         return ZKR_E_NCCL;
     }
     return ZKR_OK;
@@ -126,10 +135,14 @@ extern "C" int zkr_comm_create(zkr_ctx* ctx, int rank, int world, size_t max_ele
         delete c;
         return cuda_fail(e, "cudaMalloc(comm slab)", __FILE__, __LINE__);
     }
-    cudaMemset(c->slab, 0, kCommHeaderBytes);
-    cudaMalloc(&c->d_err, sizeof(int));
-    cudaMemset(c->d_err, 0, sizeof(int));
-    cudaMalloc(&c->d_small, 512);
+    if ((e = cudaMalloc(&c->d_err, sizeof(int))) != cudaSuccess || (e = cudaMalloc(&c->d_small, 512)) != cudaSuccess ||
+        (e = cudaMemset(c->slab, 0, kCommHeaderBytes)) != cudaSuccess || (e = cudaMemset(c->d_err, 0, sizeof(int))) != cudaSuccess) {
+        cudaFree(c->slab);
+        cudaFree(c->d_err);
+        cudaFree(c->d_small);
+        delete c;
+        return cuda_fail(e, "zkr_comm_create (flag / staging buffers)", __FILE__, __LINE__);
+    }
     c->peer_slab[rank] = c->slab;
     c->connected = world == 1;
     ZKR_CUDA(cudaDeviceSynchronize());
@@ -233,6 +246,7 @@ extern "C" void zkr_comm_destroy(zkr_comm* c) {
 // ---------------------------------------------------------------------------------------------- MSM
 extern "C" int zkr_msm_sharded(zkr_comm* c, const zkr_bases* b, const void* scalars, size_t n_local,
                                int scalars_on_device, void* out_affine) {
+    if (c && c->dead) return comm_check(c, c->ctx->user_stream);
     if (!c || !c->connected || !b || !out_affine || (!scalars && n_local) || bases_ctx(b) != c->ctx ||
         n_local != bases_n_src(b)) {
         set_error("zkr_msm_sharded: bad arguments (scalar count must equal this rank's loaded points)");
@@ -279,6 +293,7 @@ extern "C" int zkr_ntt_sharded_rows_log(int log_n, int world) {
 
 extern "C" int zkr_ntt_sharded(zkr_comm* c, int log_n, int mode, int src_buf) {
     if (!c || !c->connected || src_buf < 0 || src_buf > 1) return ZKR_E_INVALID;
+    if (c->dead) return comm_check(c, c->ctx->user_stream);
     const int base_mode = mode & 0xf;
     const bool br_out = mode & ZKR_NTT_BITREV_OUT, br_in = mode & ZKR_NTT_BITREV_IN;
     if (base_mode > 3 || br_out == br_in) {

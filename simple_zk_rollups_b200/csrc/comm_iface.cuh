@@ -23,6 +23,7 @@ struct zkr_comm {
     int* d_err = nullptr;                 // device flag: a barrier timed out
     char* d_small = nullptr;              // 512 B: partial (256) | affine result (256) of a sharded MSM
     bool connected = false;
+    bool dead = false;                    // a barrier timed out: epochs may have diverged, the comm must be re-created
 };
 
 namespace zkr {

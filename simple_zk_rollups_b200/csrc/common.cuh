@@ -48,7 +48,7 @@ constexpr int kNumStreams = 6;
 
 // Per-kernel device timing for bench.py's roofline: rings of CUDA event pairs recorded on the
 // launching stream around selected kernels while profiling is enabled.
-enum ProfId { PROF_ACCUM_G1 = 0, PROF_ACCUM_G2 = 1, PROF_NTT_PASS = 2, PROF_COUNT = 3 };
+enum ProfId { PROF_ACCUM_G1 = 0, PROF_ACCUM_G2 = 1, PROF_NTT_PASS = 2, PROF_NTT_XCHG = 3, PROF_COUNT = 4 };
 constexpr int kProfRing = 512;
 struct ProfRing {
     cudaEvent_t ev[2 * kProfRing] = {};

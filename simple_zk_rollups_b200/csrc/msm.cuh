@@ -18,8 +18,10 @@
 //     many threads.
 //   * reduction sum_b (b+1) B_b without a serial running sum: row / column sums of the bucket array viewed as a
 //     2^lr x 2^lc matrix, then bit-decomposed weighted sums (k_bucket_sums / k_bucket_weighted below).
-//   * measured dead end: capping the G2 accumulation kernel at 168 / 128 registers (3 / 4 CTAs per SM instead of 2,
-//     ~90 / ~270 spilled words per addition) makes the 2^20 proof slower, 17.8 / 18.3 ms against 17.3 ms.
+//   * measured dead ends: capping the G2 accumulation kernel at 168 / 128 registers (3 / 4 CTAs per SM instead of 2,
+//     ~90 / ~270 spilled words per addition) makes the 2^20 proof slower, 17.8 / 18.3 ms against 17.3 ms; keeping the
+//     accumulator's ZZ / ZZZ in shared memory by hand (168 registers, no spills) is slower too, 17.66 against 16.98 ms
+//     (profiles/r02_g2_smem_acc_ab.json; that kernel was deleted).
 #pragma once
 #include <cstdlib>
 
@@ -180,143 +182,6 @@ k_accum_affine(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ v
             head_key = cur;
         } else {
             acc.store(bnd + 2 * t + 1);
-            tail_key = cur;
-        }
-    }
-    bnd_keys[2 * t] = head_key;
-    bnd_keys[2 * t + 1] = tail_key;
-}
-
-// ------------------------------------------------------------------------------------------------
-// EXPERIMENT (default off, ZKR_G2_SMEM_ACC=1, G2 only): level-1 accumulation with the accumulator's ZZ / ZZZ
-// coordinates in shared memory instead of registers.
-// Why: k_accum_affine<Fq2> needs 252 registers -> 2 CTAs/SM = 2 warps per scheduler, fma pipe 36.5 % active against
-// 45.5 % for the 128-register G1 instance (profiles/r01_ncu_full_summary.md).  Capping registers makes ptxas spill
-// ~90 words per addition to local memory and is slower (measured).  Here the two coordinates that are touched only
-// twice per addition (read for U2 / S2, read-modify-write at the end) are placed in shared memory by hand: word-major
-// [16 words][blockDim] per coordinate (conflict free), 16 KB per CTA; ptxas then fits 168 registers = 3 CTAs/SM with
-// 62 B of spill stores in the whole kernel.  Same algorithm and results as k_accum_affine: parity-green on a B200 for
-// the two smallest cases of tests/test_gpu_msm.py::test_g2_smem_accumulator_experiment (all scalar sets, duplicates /
-// opposites / infinities) with the last GPU seconds of round 1; NOT yet timed.  The test is skipped unless
-// ZKR_RUN_EXPERIMENTS=1; tools/gpu_jobs/r02a.sh runs all of it and the A/B timing.
-template <class F>
-struct SmemCoord {                       // one field element per thread, word-major in shared memory
-    uint32_t* base;                      // &plane[threadIdx.x]
-    int stride;                          // blockDim.x
-    static constexpr int W = sizeof(F) / 4;
-    __device__ __forceinline__ F get() const {
-        F r;
-        uint32_t* w = reinterpret_cast<uint32_t*>(&r);
-#pragma unroll
-        for (int i = 0; i < W; i++) w[i] = base[i * stride];
-        return r;
-    }
-    __device__ __forceinline__ void set(const F& v) const {
-        const uint32_t* w = reinterpret_cast<const uint32_t*>(&v);
-#pragma unroll
-        for (int i = 0; i < W; i++) base[i * stride] = w[i];
-    }
-};
-
-template <class F>
-__global__ void __launch_bounds__(kAccumThreads, 3)
-k_accum_affine_smz(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint32_t total, int logL,
-                   const char* __restrict__ table, XYZZ<F>* __restrict__ buckets, XYZZ<F>* __restrict__ bnd,
-                   uint32_t* __restrict__ bnd_keys, uint32_t sentinel) {
-    extern __shared__ uint32_t sm[];
-    constexpr size_t AB = 2 * sizeof(F);
-    constexpr int W = sizeof(F) / 4;
-    const int L = 1 << logL, LP = L + 1;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t* sk = sm + warp * 2 * 32 * LP;
-    uint32_t* sv = sk + 32 * LP;
-    uint32_t* acc_sm = sm + (kAccumThreads / 32) * 2 * 32 * LP;          // [2][W][kAccumThreads]
-    const SmemCoord<F> ZZ = {acc_sm + threadIdx.x, kAccumThreads};
-    const SmemCoord<F> ZZZ = {acc_sm + W * kAccumThreads + threadIdx.x, kAccumThreads};
-    const size_t wchunk = (size_t)blockIdx.x * (kAccumThreads / 32) + warp;
-    const size_t wbase = wchunk * 32 * L;
-    for (int i = lane; i < 32 * L; i += 32) {
-        size_t e = wbase + i;
-        uint32_t kk = sentinel, vv = 0;
-        if (e < total) {
-            kk = keys[e];
-            vv = vals[e];
-        }
-        int r = i >> logL, ci = i & (L - 1);
-        sk[r * LP + ci] = kk;
-        sv[r * LP + ci] = vv;
-    }
-    __syncwarp();
-    const uint32_t* mk = sk + lane * LP;
-    const uint32_t* mv = sv + lane * LP;
-    const size_t t = wchunk * 32 + lane;
-
-    F ax = F::zero(), ay = F::zero();    // X, Y of the accumulator; ZZ, ZZZ live in shared memory
-    bool inf = true;
-    uint32_t cur = mk[0];
-    bool first_run = true;
-    uint32_t head_key = sentinel, tail_key = sentinel;
-    auto flush = [&](XYZZ<F>* dst) {
-        XYZZ<F> o;
-        if (inf) o = XYZZ<F>::identity();
-        else o = {ax, ay, ZZ.get(), ZZZ.get()};
-        o.store(dst);
-    };
-    for (int j = 0; j < L; j++) {
-        const uint32_t key = mk[j];
-        if (!(key < sentinel)) break;
-        const uint32_t v = mv[j];
-        if (key != cur) {
-            if (first_run) {
-                flush(bnd + 2 * t);
-                head_key = cur;
-                first_run = false;
-            } else {
-                flush(buckets + cur);
-            }
-            inf = true;
-            cur = key;
-        }
-        Affine<F> q = Affine<F>::load_ro(table + AB * (size_t)(v & ~kNegBit));
-        if (v & kNegBit) q.y = q.y.neg();
-        if (inf) {
-            ax = q.x;
-            ay = q.y;
-            ZZ.set(F::one());
-            ZZZ.set(F::one());
-            inf = false;
-            continue;
-        }
-        const F p = q.x * ZZ.get() - ax;
-        const F r = q.y * ZZZ.get() - ay;
-        if (p.is_zero()) {
-            if (r.is_zero()) {
-                const XYZZ<F> d = XYZZ<F>::dbl_affine(q);
-                inf = d.is_inf();
-                ax = d.x;
-                ay = d.y;
-                ZZ.set(d.zz);
-                ZZZ.set(d.zzz);
-            } else {
-                inf = true;
-            }
-            continue;
-        }
-        const F pp = p.sqr();
-        const F ppp = p * pp;
-        const F qq = ax * pp;
-        const F x3 = r.sqr() - ppp - qq.dbl();
-        ay = r * (qq - x3) - ay * ppp;
-        ax = x3;
-        ZZ.set(ZZ.get() * pp);
-        ZZZ.set(ZZZ.get() * ppp);
-    }
-    if (cur < sentinel) {
-        if (first_run) {
-            flush(bnd + 2 * t);
-            head_key = cur;
-        } else {
-            flush(bnd + 2 * t + 1);
             tail_key = cur;
         }
     }
@@ -707,8 +572,6 @@ int bases_build(zkr_ctx* ctx, zkr_bases* b, const char* h_points, size_t n_src, 
     ZKR_CUDA(cudaFuncSetAttribute(k_bucket_weighted<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(XB * kReduceThreads)));
     ZKR_CUDA(cudaFuncSetAttribute((k_accum_affine<F, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
     ZKR_CUDA(cudaFuncSetAttribute((k_accum_affine<F, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
-    if constexpr (sizeof(F) == 64)
-        ZKR_CUDA(cudaFuncSetAttribute(k_accum_affine_smz<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
     ZKR_CUDA(cudaStreamSynchronize(st));
     return ZKR_OK;
 }
@@ -739,18 +602,8 @@ int msm_run(zkr_ctx* ctx, cudaStream_t st, const zkr_bases* b, const uint32_t* d
     const size_t smem = (size_t)(kAccumThreads / 32) * 2 * 32 * (L + 1) * 4;
     XYZZ<F>* buckets = (XYZZ<F>*)wk.buckets;
     const int pslot = ctx->prof_begin(sizeof(F) == 32 ? PROF_ACCUM_G1 : PROF_ACCUM_G2, st, (double)total);
-    bool smz = false;
-    if constexpr (sizeof(F) == 64) {
-        const char* e = getenv("ZKR_G2_SMEM_ACC");       // experiment knob, read per call so that a test can toggle it
-        smz = e && atoi(e) != 0;
-        if (smz)
-            ZKR_LAUNCH(ctx, k_accum_affine_smz<F>, b->T1p / kAccumThreads, kAccumThreads,
-                       smem + 2 * sizeof(F) * kAccumThreads, st, dk.Current(), dv.Current(), total, b->logL, b->table, buckets,
-                       (XYZZ<F>*)wk.bnd[0], wk.bnd_keys[0], nb);
-    }
-    if (!smz)
-        ZKR_LAUNCH(ctx, (k_accum_affine<F, kPrefetch>), b->T1p / kAccumThreads, kAccumThreads, smem, st, dk.Current(),
-                   dv.Current(), total, b->logL, b->table, buckets, (XYZZ<F>*)wk.bnd[0], wk.bnd_keys[0], nb);
+    ZKR_LAUNCH(ctx, (k_accum_affine<F, kPrefetch>), b->T1p / kAccumThreads, kAccumThreads, smem, st, dk.Current(),
+               dv.Current(), total, b->logL, b->table, buckets, (XYZZ<F>*)wk.bnd[0], wk.bnd_keys[0], nb);
     ctx->prof_end(sizeof(F) == 32 ? PROF_ACCUM_G1 : PROF_ACCUM_G2, pslot, st);
     // boundary levels
     size_t cnt = 2 * (size_t)b->T1p;

@@ -38,6 +38,10 @@ int bases_range_error(const zkr_bases* b, cudaStream_t st, int* err) {
     if (*err) ZKR_CUDA(cudaMemsetAsync(b->work.range_err, 0, sizeof(int), st));
     return ZKR_OK;
 }
+int bases_range_clear(const zkr_bases* b, cudaStream_t st) {
+    if (b && b->work.range_err) ZKR_CUDA(cudaMemsetAsync(b->work.range_err, 0, sizeof(int), st));
+    return ZKR_OK;
+}
 // white-box test hook: copy an internal device buffer to the host
 int bases_peek(const zkr_bases* b, int what, size_t offset, void* out, size_t bytes) {
     const MsmWork& w = b->work;

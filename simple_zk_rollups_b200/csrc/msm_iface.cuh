@@ -20,6 +20,7 @@ int g1_result_to_affine_std(zkr_ctx*, cudaStream_t, const void* d_xyzz, void* d_
 int g2_result_to_affine_std(zkr_ctx*, cudaStream_t, const void* d_xyzz, void* d_out128);
 void bases_release(zkr_bases* b);
 int bases_range_error(const zkr_bases* b, cudaStream_t st, int* err);
+int bases_range_clear(const zkr_bases* b, cudaStream_t st);   // asynchronous, ordered on st
 void bases_info(const zkr_bases* b, uint64_t* n, int* c, int* W, uint64_t* bytes);
 void* bases_result_buf(const zkr_bases* b);
 uint64_t bases_n_src(const zkr_bases* b);

@@ -17,6 +17,7 @@
 //   * data may be in standard OR Montgomery form: every constant (twiddles, scalings) is stored in
 //     Montgomery form and mont_mul(x, cR) = x*c keeps the form of x.
 #include <cstdlib>
+#include <cstring>
 
 #include "ntt_iface.cuh"
 
@@ -73,6 +74,24 @@ __global__ void k_pow_table(Fr* out, unsigned count, const Fr* base, unsigned lo
     Fr v = fr_pow(*base, (unsigned long long)i * stride);
     if (cst) v = v * *cst;
     v.store(out + i);
+}
+
+// out[p] = c * g^j(p), standard form; c, g standard form.  j(p) = start + p (world_log < 0) or the transform index of
+// local element p of rank's COLS slab (see k_scale_pow_sharded, layout 0).  Workload generator: a dense vector whose
+// transform has a closed form on the host, X[k] = c (g^N - 1) / (g w^k - 1)  (bench.py, tests).
+__global__ void k_fill_geometric(Fr* out, size_t n_local, const Fr* cg, unsigned long long start, int s0, int world_log,
+                                 int rank) {
+    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_local) return;
+    unsigned long long j;
+    if (world_log < 0) {
+        j = start + p;
+    } else {
+        const int cl = s0 - world_log;
+        j = ((p >> cl) << s0) + ((unsigned long long)rank << cl) + (p & (((size_t)1 << cl) - 1));
+    }
+    const Fr c = Fr::load(cg), g = Fr::load(cg + 1).to_mont();
+    (c * fr_pow(g, j)).store(out + p);
 }
 
 __device__ __forceinline__ int slot_of(int e) { return e + (e >> 3); }
@@ -427,12 +446,14 @@ static int launch_pass(zkr_ctx* ctx, cudaStream_t st, const NttTables* t, Fr* da
     const int tile = 1 << (g.k + g.c);
     const int threads = tile / 8;
     const size_t smem = (size_t)8 * (tile + (tile >> 3) + 4) * sizeof(uint32_t);
-    const int pslot = ctx->prof_begin(PROF_NTT_PASS, st, prof_units);
+    // the pass whose write-back is the all-to-all (remote stores) is timed on its own: bench.py's exchange GB/s
+    const int pid = (MODE == 1 || MODE == 2) ? PROF_NTT_XCHG : PROF_NTT_PASS;
+    const int pslot = ctx->prof_begin(pid, st, prof_units);
     if (dit) ZKR_LAUNCH(ctx, (k_ntt_pass<true, MODE == 1 ? 3 : MODE>), g.blocks, threads, smem, st, data, g.k, g.c, g.s,
                         g.ls, g.chunk_log, g.ctw, W, t->kw, tlo, thi, t->lb, g.tw_shift, xp);
     else ZKR_LAUNCH(ctx, (k_ntt_pass<false, (MODE == 2 || MODE == 3) ? 0 : MODE>), g.blocks, threads, smem, st, data, g.k, g.c, g.s,
                     g.ls, g.chunk_log, g.ctw, W, t->kw, tlo, thi, t->lb, g.tw_shift, xp);
-    ctx->prof_end(PROF_NTT_PASS, pslot, st);
+    ctx->prof_end(pid, pslot, st);
     return ZKR_OK;
 }
 
@@ -646,6 +667,31 @@ extern "C" int zkr_ntt(zkr_ctx* ctx, void* data, int log_n, int mode, int on_dev
         ZKR_CUDA(cudaMemcpyAsync(data, d, bytes, cudaMemcpyDeviceToHost, st));
         ZKR_CUDA(cudaStreamSynchronize(st));
     }
+    return ZKR_OK;
+}
+
+extern "C" int zkr_fill_geometric(zkr_ctx* ctx, void* d_out, size_t n_local, const void* c32, const void* g32,
+                                  uint64_t start, int log_n, int world, int rank) {
+    if (!ctx || !d_out || !c32 || !g32 || world < 1 || (world & (world - 1)) || rank < 0 || rank >= world) return ZKR_E_INVALID;
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = ctx->user_stream;
+    void* p;
+    ZKR_TRY(ctx->scratch_get("fill_cg", 64, &p));
+    char cg[64];
+    memcpy(cg, c32, 32);
+    memcpy(cg + 32, g32, 32);
+    ZKR_CUDA(cudaMemcpyAsync(p, cg, 64, cudaMemcpyHostToDevice, st));
+    ZKR_CUDA(cudaStreamSynchronize(st));   // cg is a stack buffer
+    int wl = -1, s0 = 0;
+    if (world > 1) {
+        wl = 0;
+        while ((1 << wl) < world) wl++;
+        s0 = log_n - ntt_sharded_k0(log_n, wl);
+        if (log_n < wl || n_local != ((size_t)1 << (log_n - wl)) || s0 < wl) return ZKR_E_INVALID;
+    }
+    if (n_local)
+        ZKR_LAUNCH(ctx, k_fill_geometric, ceil_div(n_local, 128), 128, 0, st, (Fr*)d_out, n_local, (const Fr*)p, start, s0,
+                   wl, rank);
     return ZKR_OK;
 }
 

@@ -12,6 +12,8 @@
 //   pi_c = sum_{i>l} w_i C_i - rs delta1  (one MSM)  +  sum h_j hExps_j (one MSM)  +  s pi_a + r pib1
 // The blinding terms ride inside the MSMs as extra bases, so the only scalar multiplications left
 // are s*pi_a and r*pib1 (two threads, overlapped with the G2 / C / H MSMs on other streams).
+#include <sys/random.h>
+
 #include <cstdlib>
 #include <cstring>
 #include <thread>
@@ -543,6 +545,55 @@ static int check_range_flags(zkr_ctx* ctx, const zkr_pkey* pk) {
     return ZKR_OK;
 }
 
+// Blinding scalar for a caller that passed NULL: uniform in [0, r) from the OS CSPRNG (getrandom), by rejection on
+// 254-bit draws -- what websnark's groth16GenProof does internally.  The snarkjs debug mode (r = s = 0, deterministic,
+// not zero-knowledge) has to be asked for with explicit zero buffers.
+static int draw_scalar(void* out32) {
+    static const uint32_t kR[8] = {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u,
+                                   0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+    for (int tries = 0; tries < 256; tries++) {
+        uint32_t v[8];
+        size_t got = 0;
+        while (got < sizeof(v)) {
+            ssize_t k = getrandom((char*)v + got, sizeof(v) - got, 0);
+            if (k < 0) {
+                set_error("getrandom failed: no entropy source for the blinding scalars");
+                return ZKR_E_INVALID;
+            }
+            got += (size_t)k;
+        }
+        v[7] &= 0x3fffffffu;
+        bool less = false;
+        for (int i = 7; i >= 0; i--) {
+            if (v[i] != kR[i]) {
+                less = v[i] < kR[i];
+                break;
+            }
+        }
+        if (less) {
+            memcpy(out32, v, 32);
+            return ZKR_OK;
+        }
+    }
+    return ZKR_E_INVALID;
+}
+static int stage_blinding(char* dst64, const void* r32, const void* s32) {
+    if (r32) memcpy(dst64, r32, 32);
+    else ZKR_TRY(draw_scalar(dst64));
+    if (s32) memcpy(dst64 + 32, s32, 32);
+    else ZKR_TRY(draw_scalar(dst64 + 32));
+    return ZKR_OK;
+}
+
+// Forget range flags left behind by earlier asynchronous proofs nobody checked (zkr_prove_dev without
+// zkr_prove_check): a blocking call must report on ITS inputs only.
+static int clear_range_flags(zkr_ctx* ctx, const zkr_pkey* pk) {
+    ZKR_CUDA(cudaMemsetAsync(pk->err, 0, sizeof(int), ctx->user_stream));
+    const zkr_bases* bs[] = {pk->A, pk->B1, pk->B2, pk->C, pk->H};
+    for (const zkr_bases* b : bs) ZKR_TRY(bases_range_clear(b, ctx->user_stream));
+    return ZKR_OK;
+}
+
 static int prove_host(zkr_ctx* ctx, const zkr_pkey* pk, const void* witness, size_t n_signals, const void* r32,
                       const void* s32, void* out_proof, zkr_stats* stats, zkr_comm* comm) {
     if (!ctx || !pk || !witness || !out_proof || pk->ctx != ctx) return ZKR_E_INVALID;
@@ -558,10 +609,9 @@ static int prove_host(zkr_ctx* ctx, const zkr_pkey* pk, const void* witness, siz
     cudaStream_t us = ctx->user_stream;
     const uint64_t launches0 = ctx->launches;
     char* pin = (char*)pk->pinned;
-    memset(pin + 256, 0, 64);
-    if (r32) memcpy(pin + 256, r32, 32);
-    if (s32) memcpy(pin + 288, s32, 32);
+    ZKR_TRY(stage_blinding(pin + 256, r32, s32));
     cudaEvent_t const* ev = pk->ev;
+    ZKR_TRY(clear_range_flags(ctx, pk));
     cudaEventRecord(ev[14], us);
     ZKR_CUDA(cudaMemcpyAsync(pk->wext, witness, 32ull * pk->n_vars, cudaMemcpyHostToDevice, us));
     ZKR_CUDA(cudaMemcpyAsync(pk->rs_dev, pin + 256, 64, cudaMemcpyHostToDevice, us));
@@ -603,6 +653,10 @@ extern "C" int zkr_prove(zkr_ctx* ctx, const zkr_pkey* pk, const void* witness, 
 extern "C" int zkr_prove_sharded(zkr_comm* comm, const zkr_pkey* pk, const void* witness, size_t n_signals,
                                  const void* r32, const void* s32, void* out_proof, zkr_stats* stats) {
     if (!comm) return ZKR_E_INVALID;
+    if (!r32 || !s32) {
+        set_error("zkr_prove_sharded: r32 and s32 are required (every rank must use the same blinding scalars)");
+        return ZKR_E_INVALID;
+    }
     return prove_host(comm->ctx, pk, witness, n_signals, r32, s32, out_proof, stats, comm);
 }
 
@@ -615,12 +669,19 @@ extern "C" int zkr_prove_dev(zkr_ctx* ctx, const zkr_pkey* pk, const void* d_wit
     char* pin = (char*)pk->pinned;
     // the staging words are re-used per call: wait for the previous call's copy to have been consumed
     ZKR_CUDA(cudaStreamSynchronize(us));
-    memset(pin + 256, 0, 64);
-    if (r32) memcpy(pin + 256, r32, 32);
-    if (s32) memcpy(pin + 288, s32, 32);
+    ZKR_TRY(stage_blinding(pin + 256, r32, s32));
     ZKR_CUDA(cudaMemcpyAsync(pk->wext, d_witness, 32ull * pk->n_vars, cudaMemcpyDeviceToDevice, us));
     ZKR_CUDA(cudaMemcpyAsync(pk->rs_dev, pin + 256, 64, cudaMemcpyHostToDevice, us));
     return prove_enqueue(ctx, pk, (char*)d_out_proof, false);
+}
+
+// zkr_prove_dev is asynchronous and cannot return ZKR_E_WITNESS_RANGE itself: the device-side flags (witness value or
+// blinding scalar >= r, witness[0] != 1) stay set until they are read here.  Synchronises the ctx stream, reports and
+// clears them: ZKR_OK means every zkr_prove_dev on this key since the last check had valid inputs.
+extern "C" int zkr_prove_check(zkr_ctx* ctx, const zkr_pkey* pk) {
+    if (!ctx || !pk || pk->ctx != ctx) return ZKR_E_INVALID;
+    DeviceGuard g(ctx->device);
+    return check_range_flags(ctx, pk);
 }
 
 // All proofs assigned to one context, pipelined: while proof k runs, the witness of proof k+1 is uploaded into the
@@ -653,14 +714,15 @@ static int prove_batch_ctx(zkr_ctx* ctx, const zkr_pkey* pk, const void* const* 
             return ZKR_E_INVALID;
         }
     // everything queued on the user stream so far (a previous proof on this key) must be done with buf[0]
+    ZKR_TRY(clear_range_flags(ctx, pk));
     ZKR_CUDA(cudaStreamSynchronize(us));
     ZKR_CUDA(cudaMemcpyAsync(buf[0], witnesses[first], wbytes, cudaMemcpyHostToDevice, cs));
     ZKR_CUDA(cudaEventRecord(pk->ev_up[0], cs));
     int k = 0;
     for (int i = first; i < n_proofs; i += stride, k++) {
         const int cur = k & 1;
-        memset(pin + 256, 0, 64);
-        if (rs32) memcpy(pin + 256, (const char*)rs32 + 64ull * i, 64);
+        ZKR_TRY(stage_blinding(pin + 256, rs32 ? (const char*)rs32 + 64ull * i : nullptr,
+                               rs32 ? (const char*)rs32 + 64ull * i + 32 : nullptr));
         ZKR_CUDA(cudaStreamWaitEvent(us, pk->ev_up[cur], 0));
         ZKR_CUDA(cudaMemcpyAsync(pk->rs_dev, pin + 256, 64, cudaMemcpyHostToDevice, us));
         ZKR_TRY(prove_enqueue(ctx, pk, pk->proof, false, nullptr, buf[cur]));

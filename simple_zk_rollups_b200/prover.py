@@ -95,9 +95,10 @@ class Groth16Prover:
         self._keys.append(h)
         return h
 
-    def prove_sharded(self, comm, key, witness_bin, r=0, s=0):
+    def prove_sharded(self, comm, key, witness_bin, r, s):
         """comm: sharding.Comm of this rank (all ranks call with the same witness, r, s) -> (proof, stats);
-        every rank returns the same 256 bytes as prove() on one GPU."""
+        every rank returns the same 256 bytes as prove() on one GPU.  r, s are required: the ranks must agree on them,
+        so the caller draws them once (secrets.randbelow(r)) and hands the same pair to every rank."""
         w = np.frombuffer(witness_bin, dtype=np.uint8) if isinstance(witness_bin, (bytes, bytearray)) else witness_bin
         out = np.zeros(_lib.PROOF_BYTES, dtype=np.uint8)
         st = _lib.Stats()
@@ -112,9 +113,13 @@ class Groth16Prover:
         _lib.check(self.L.zkr_pkey_info(key, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
         return dict(nVars=a.value, nPublic=b.value, domainSize=c.value, device_bytes=d.value)
 
-    def prove(self, key, witness_bin, r=0, s=0):
-        """witness_bin: binarifyWitness output.  r, s: blinding scalars (ints < r); (0, 0) is the
-        snarkjs debug mode.  -> (256-byte proof, stats dict)."""
+    def prove(self, key, witness_bin, r=None, s=None):
+        """witness_bin: binarifyWitness output.  r, s: blinding scalars (ints < r).  None (the default) draws a fresh
+        CSPRNG scalar, as websnark's groth16GenProof does internally: proofs are zero-knowledge unless the caller
+        asks otherwise.  Pass explicit values for parity tests; (0, 0) is the snarkjs debug mode (deterministic,
+        NOT zero-knowledge).  -> (256-byte proof, stats dict)."""
+        r = _random_scalar() if r is None else r
+        s = _random_scalar() if s is None else s
         w = np.frombuffer(witness_bin, dtype=np.uint8) if isinstance(witness_bin, (bytes, bytearray)) else witness_bin
         out = np.zeros(_lib.PROOF_BYTES, dtype=np.uint8)
         st = _lib.Stats()
@@ -132,7 +137,8 @@ def prove_batch(provers, keys, witness_bins, rs=None):
     """zkr_prove_batch: n independent proofs over len(provers) contexts (one per GPU; keys[i] is the same circuit's
     key loaded on provers[i]), round-robin, one proof in flight per GPU -- the shape of many genTxVerifierProof calls
     (operator/src/snarks/tx.ts:6-10) drained by an operator batch loop.  witness_bins: list of binarifyWitness
-    outputs; rs: optional list of (r, s) ints (default 0, 0).  -> list of 256-byte proofs, in input order."""
+    outputs; rs: optional list of (r, s) ints; None draws a fresh CSPRNG pair per proof (pass [(0, 0)] * n for the
+    snarkjs debug mode).  -> list of 256-byte proofs, in input order."""
     L = provers[0].L
     n = len(witness_bins)
     if n == 0:
@@ -144,6 +150,8 @@ def prove_batch(provers, keys, witness_bins, rs=None):
     ctxs = (C.c_void_p * len(provers))(*[p.ctx for p in provers])
     pks = (C.c_void_p * len(provers))(*keys)
     wptrs = (C.c_void_p * n)(*[w.ctypes.data for w in ws])
+    if rs is None:
+        rs = [(_random_scalar(), _random_scalar()) for _ in range(n)]
     rsb = None
     if rs is not None:
         rsb = np.frombuffer(b"".join(int(r).to_bytes(32, "little") + int(s).to_bytes(32, "little") for r, s in rs),
@@ -168,21 +176,46 @@ def _random_scalar():
     return secrets.randbelow(SNARK_FIELD_SIZE)
 
 
-def genProof(provingKey, witness, r=None, s=None, prover=None, _key_cache={}):
+class _KeyCache:
+    """Resident keys of genProof, per (prover, key object).  The entry keeps a reference to the key object it was made
+    from, so its id() cannot be recycled for another circuit while the entry lives; byte / array keys are looked up by
+    a content hash.  Bounded: the least recently used key is freed on the device (zkr_pkey_free) when a new one would
+    exceed `limit` resident keys."""
+
+    def __init__(self, limit=4):
+        self.limit, self.entries = limit, {}
+
+    def get(self, p, provingKey):
+        import hashlib
+        if isinstance(provingKey, dict):
+            ck = (id(p), "obj", id(provingKey))
+        else:
+            buf = provingKey if isinstance(provingKey, (bytes, bytearray)) else np.ascontiguousarray(provingKey).tobytes()
+            ck = (id(p), "bin", hashlib.blake2b(buf, digest_size=16).digest(), len(buf))
+        e = self.entries.pop(ck, None)
+        if e is None or e[0] not in p._keys:             # absent, or freed behind our back (prover.close())
+            binkey = binarifyProvingKey(provingKey) if isinstance(provingKey, dict) else provingKey
+            key = p.load_key(binkey)
+            e = (key, p.key_info(key)["nPublic"], provingKey if isinstance(provingKey, dict) else None, p)
+            while len(self.entries) >= self.limit:
+                old_key, _, _, old_p = self.entries.pop(next(iter(self.entries)))
+                if old_key in old_p._keys:
+                    old_p.L.zkr_pkey_free(old_key)
+                    old_p._keys.remove(old_key)
+        self.entries[ck] = e                             # re-inserted last: most recently used
+        return e[0], e[1]
+
+
+_key_cache = _KeyCache()
+
+
+def genProof(provingKey, witness, r=None, s=None, prover=None):
     """snarkjs groth.genProof shape: -> {"proof": {pi_a, pi_b, pi_c, protocol}, "publicSignals": [...]}.
-    provingKey: snarkjs pk JSON (dict) or an already-binarified key (bytes / uint8 array).
-    r, s default to CSPRNG draws like websnark; pass 0, 0 for the snarkjs debug mode."""
+    provingKey: snarkjs pk JSON (dict) or an already-binarified key (bytes / uint8 array); the resident key is cached
+    per (prover, key) -- callers that prove in a loop should still load the key once (Groth16Prover.load_key) and call
+    prove() with the handle.  r, s default to CSPRNG draws like websnark; pass 0, 0 for the snarkjs debug mode."""
     p = prover or default_prover()
-    if isinstance(provingKey, dict):
-        ck = id(provingKey)
-        if ck not in _key_cache:
-            _key_cache[ck] = (p.load_key(binarifyProvingKey(provingKey)), int(provingKey["nPublic"]))
-        key, n_public = _key_cache[ck]
-    else:
-        key = p.load_key(provingKey)
-        n_public = p.key_info(key)["nPublic"]
-    r = _random_scalar() if r is None else r
-    s = _random_scalar() if s is None else s
+    key, n_public = _key_cache.get(p, provingKey)
     buf, _ = p.prove(key, binarifyWitness(witness), r, s)
     return {"proof": proof_from_bytes(buf), "publicSignals": [str(int(x)) for x in witness[1:n_public + 1]]}
 
@@ -221,9 +254,7 @@ def createProofGenerator(provingKey, verifyingKey, circuitName, calculateWitness
     def generate(circuitInputs, r=None, s=None):
         witness, n_pub = calculateWitness(circuitName, circuitInputs)
         publicSignals = witness[1:n_pub + 1]
-        rr = _random_scalar() if r is None else r
-        ss = _random_scalar() if s is None else s
-        buf, _ = p.prove(key, binarifyWitness(witness), rr, ss)
+        buf, _ = p.prove(key, binarifyWitness(witness), r, s)
         proof = proof_from_bytes(buf)
         if isValid is not None and not isValid(verifyingKey, proof, publicSignals):
             raise RuntimeError("Invalid proof generated")

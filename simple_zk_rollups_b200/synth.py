@@ -97,12 +97,17 @@ def witness_bytes(witness):
     return b"".join(int(x).to_bytes(32, "little") for x in witness)
 
 
-def generate(n_constraints, n_public, seed=0, n_free=3, bit_every=33):
-    """-> (R1CS, witness list[int]).  Deterministic in (n_constraints, n_public, seed)."""
+def generate(n_constraints, n_public, seed=0, n_free=3, bit_every=33, witness_seed=None):
+    """-> (R1CS, witness list[int]).  Deterministic in (n_constraints, n_public, seed, witness_seed).
+    witness_seed = None: one generator draws structure and input values (the round-1 behaviour every committed fixture
+    was made with).  witness_seed = k: the input and bit values come from a second generator, so the same
+    (n_constraints, n_public, seed) gives the SAME circuit for every k and a different satisfying witness per k
+    (distinct proofs under one proving key: BASELINE.json configs[4])."""
     rng = random.Random((0x7A6B726F6C6C7570 ^ seed) & 0xFFFFFFFFFFFFFFFF)
+    wrng = rng if witness_seed is None else random.Random((0x7769746E65737300 ^ (seed << 20) ^ witness_seed) & 0xFFFFFFFFFFFFFFFF)
     pool = [1, R - 1] + [rng.randrange(R) for _ in range(N_ROUND_CONSTANTS)]
     ONE, P_ONE, P_NEG = 0, 0, 1
-    w = [1] + [rng.randrange(R) for _ in range(n_public + n_free)]
+    w = [1] + [wrng.randrange(R) for _ in range(n_public + n_free)]
     n_in = n_public + n_free
     ent = {"A": ([], [], []), "B": ([], [], []), "C": ([], [], [])}
 
@@ -129,7 +134,7 @@ def generate(n_constraints, n_public, seed=0, n_free=3, bit_every=33):
     while row < n_constraints:
         if bit_every and row % bit_every == bit_every - 1:
             b = len(w)
-            w.append(rng.getrandbits(1))
+            w.append(wrng.getrandbits(1))
             put("A", row, b, P_ONE)
             put("B", row, ONE, P_NEG)
             put("B", row, b, P_ONE)

@@ -1,6 +1,15 @@
 // N-API addon: the thin shim between the reference's TypeScript host and libzkr's C-ABI.
 // SOURCE ONLY in this repository -- node and node_api.h are not present in the build image, so this
-// file is not compiled or tested here (the C-ABI it calls is, from Python, in tests/).
+// file is only syntax-checked here against a declarations-only stub of node_api.h (tests/test_abi.py); the C-ABI
+// it calls is tested from Python in tests/.
+//
+// Threading.  zkr.h requires the calls on one zkr_ctx to be serialised, and a zkr_pkey carries the work buffers of
+// ONE proof in flight.  JS is free to overlap calls (two `await zkr.prove(...)` from concurrent Express requests,
+// Promise.all, the tx and the withdraw generator together; a synchronous verify on the main thread while a prove
+// runs on a libuv worker), so every zkr_* call on g_ctx below takes g_mu: proofs run one at a time per process,
+// in the order the workers get the lock, and a key cannot be freed (GC finalizer) under a running proof.  One GPU
+// holds one proof at a time anyway (the five-stream proof saturates it); to use several GPUs run one
+// process per GPU or call zkr_prove_batch.
 // Build (on a machine with node >= 12 and libzkr.so):
 //   g++ -O2 -fPIC -shared -I$(node -p "require('node-addon-api').include_dir" || echo .) \
 //       -I<node>/include/node -I../../include zkr_napi.cc -o zkr_napi.node -L.. -lzkr -Wl,-rpath,'$ORIGIN/..'
@@ -17,6 +26,7 @@
 #include <node_api.h>
 
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -25,8 +35,11 @@
 namespace {
 
 zkr_ctx* g_ctx = nullptr;
+std::mutex g_mu;             // serialises every zkr_* call on g_ctx (see "Threading" above)
+using Lock = std::lock_guard<std::mutex>;
 
 bool ensure_ctx(napi_env env) {
+    Lock lk(g_mu);
     if (g_ctx) return true;
     int rc = zkr_ctx_create(0, &g_ctx);
     if (rc != ZKR_OK) {
@@ -36,7 +49,10 @@ bool ensure_ctx(napi_env env) {
     return true;
 }
 
-void free_key(napi_env, void* data, void*) { zkr_pkey_free(static_cast<zkr_pkey*>(data)); }
+void free_key(napi_env, void* data, void*) {
+    Lock lk(g_mu);
+    zkr_pkey_free(static_cast<zkr_pkey*>(data));
+}
 
 napi_value LoadKey(napi_env env, napi_callback_info info) {
     size_t argc = 1;
@@ -50,7 +66,11 @@ napi_value LoadKey(napi_env env, napi_callback_info info) {
     }
     if (!ensure_ctx(env)) return nullptr;
     zkr_pkey* pk = nullptr;
-    int rc = zkr_pkey_load_bin(g_ctx, buf, len, &pk);
+    int rc;
+    {
+        Lock lk(g_mu);
+        rc = zkr_pkey_load_bin(g_ctx, buf, len, &pk);
+    }
     if (rc != ZKR_OK) {
         napi_throw_error(env, "ZKR_BADKEY", zkr_last_error());
         return nullptr;
@@ -72,7 +92,12 @@ napi_value LoadKeyJson(napi_env env, napi_callback_info info) {
     }
     if (!ensure_ctx(env)) return nullptr;
     zkr_pkey* pk = nullptr;
-    if (zkr_pkey_load_json(g_ctx, static_cast<const char*>(buf), len, &pk) != ZKR_OK) {
+    int rc;
+    {
+        Lock lk(g_mu);
+        rc = zkr_pkey_load_json(g_ctx, static_cast<const char*>(buf), len, &pk);
+    }
+    if (rc != ZKR_OK) {
         napi_throw_error(env, "ZKR_BADKEY", zkr_last_error());
         return nullptr;
     }
@@ -81,7 +106,10 @@ napi_value LoadKeyJson(napi_env env, napi_callback_info info) {
     return ext;
 }
 
-void free_vkey(napi_env, void* data, void*) { zkr_vkey_free(static_cast<zkr_vkey*>(data)); }
+void free_vkey(napi_env, void* data, void*) {
+    Lock lk(g_mu);
+    zkr_vkey_free(static_cast<zkr_vkey*>(data));
+}
 
 napi_value LoadVerifyingKey(napi_env env, napi_callback_info info) {
     size_t argc = 1;
@@ -95,7 +123,12 @@ napi_value LoadVerifyingKey(napi_env env, napi_callback_info info) {
     }
     if (!ensure_ctx(env)) return nullptr;
     zkr_vkey* vk = nullptr;
-    if (zkr_vkey_load_json(g_ctx, static_cast<const char*>(buf), len, &vk) != ZKR_OK) {
+    int rc;
+    {
+        Lock lk(g_mu);
+        rc = zkr_vkey_load_json(g_ctx, static_cast<const char*>(buf), len, &vk);
+    }
+    if (rc != ZKR_OK) {
         napi_throw_error(env, "ZKR_BADKEY", zkr_last_error());
         return nullptr;
     }
@@ -119,8 +152,12 @@ napi_value Verify(napi_env env, napi_callback_info info) {
         napi_throw_type_error(env, nullptr, "verify(vk, proof: Uint8Array(256), publicSignalsBin: ArrayBuffer)");
         return nullptr;
     }
-    int valid = 0;
-    if (zkr_verify(g_ctx, static_cast<zkr_vkey*>(vkv), pdata, sbuf, slen / 32, &valid) != ZKR_OK) {
+    int valid = 0, rc;
+    {
+        Lock lk(g_mu);       // waits for a proof in flight on a worker thread: the ctx's scratch and stream are shared
+        rc = zkr_verify(g_ctx, static_cast<zkr_vkey*>(vkv), pdata, sbuf, slen / 32, &valid);
+    }
+    if (rc != ZKR_OK) {
         napi_throw_error(env, "ZKR_VERIFY", zkr_last_error());      // the contract's reverts (TxVerifier.sol:261,265)
         return nullptr;
     }
@@ -142,9 +179,11 @@ struct ProveJob {
 
 void ProveExecute(napi_env, void* data) {       // worker thread
     ProveJob* j = static_cast<ProveJob*>(data);
+    Lock lk(g_mu);
+    // r / s absent: libzkr draws them from the OS CSPRNG (zkr.h), like websnark does internally
     j->rc = zkr_prove(g_ctx, j->pk, j->witness.data(), j->witness.size() / 32, j->has_r ? j->r : nullptr,
                       j->has_s ? j->s : nullptr, j->proof, nullptr);
-    if (j->rc != ZKR_OK) j->err = zkr_last_error();
+    if (j->rc != ZKR_OK) j->err = zkr_last_error();      // thread-local message: read it on this thread
 }
 
 void ProveComplete(napi_env env, napi_status, void* data) {

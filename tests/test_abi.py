@@ -68,6 +68,24 @@ def test_product_does_not_touch_the_oracle():
     subprocess.run([sys.executable, "-c", code], check=True)
 
 
+def test_napi_addon_source_compiles_and_serialises_ctx_calls():
+    """The N-API shim is shipped as source (no node in the image): compile it against a declarations-only node_api.h
+    and check that every zkr_* call on the shared context sits under the addon's mutex (zkr.h: calls on one ctx are
+    serialised by the caller; ADVICE r1: overlapping `await zkr.prove()` raced on the key's work buffers)."""
+    src = os.path.join(ROOT, "simple_zk_rollups_b200", "ts", "zkr_napi.cc")
+    p = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Wno-comment", "-Werror",
+                        "-I", os.path.join(ROOT, "tests", "csrc", "napi_stub"), "-I", os.path.join(ROOT, "include"), src],
+                       capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    lines = open(src).read().splitlines()
+    for i, ln in enumerate(lines):
+        m = re.search(r"\b(zkr_(?!last_error|strerror|ctx\b|pkey\b|vkey\b)\w+)\(", ln)
+        if not m or ln.lstrip().startswith("//"):
+            continue
+        window = "\n".join(lines[max(0, i - 6):i])
+        assert "Lock lk(g_mu)" in window, "%s at line %d is not under g_mu" % (m.group(1), i + 1)
+
+
 def test_bench_contract_flags():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--help"], capture_output=True, text=True)
     assert out.returncode == 0

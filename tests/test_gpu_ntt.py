@@ -93,3 +93,59 @@ def test_h_pipeline(zctx, log_m):
         assert got == (brev(want, log_m) if bitrev else want)
     for d in (da, db, dh):
         _lib.check(L.zkr_dev_free(zctx, d))
+
+
+@pytest.mark.parametrize("log_n", [20, 24])
+def test_ntt_horner_at_random_points(zctx, log_n):
+    """SURVEY 8(d) config 4 check at 2^20 / 2^24: uniform random input; the transformed values at 8 random indices
+    (plus the first and the last) must equal the polynomial evaluated there by Horner's rule on the host (oracle C
+    restatement, no transform code): forward X[k] = x(w^k), coset X[k] = x(g w^k), and the inverse transform's
+    coefficients evaluated back at w^k must return the input."""
+    from oracle import cbind
+    L = _lib.lib()
+    n = 1 << log_n
+    rs = np.random.RandomState(100 + log_n)
+    x = rs.randint(0, 256, size=n * 32, dtype=np.uint8)
+    x.reshape(n, 32)[:, 31] &= 0x1F                          # < 2^253 < r
+    w, gsh = g.root_of_unity(log_n), g.root_of_unity(log_n + 1)
+    rng = random.Random(log_n)
+    ks = [0, n - 1] + [rng.randrange(n) for _ in range(8)]
+    val = lambda buf, k: int.from_bytes(buf[32 * k:32 * k + 32].tobytes(), "little")
+    fwd = x.copy()
+    _lib.check(L.zkr_ntt(zctx, _lib.buf_ptr(fwd), log_n, FWD, 0))
+    for k in ks:
+        assert val(fwd, k) == cbind.horner(x, pow(w, k, R)), "forward, index %d" % k
+    del fwd
+    cf = x.copy()
+    _lib.check(L.zkr_ntt(zctx, _lib.buf_ptr(cf), log_n, CFWD, 0))
+    for k in ks[:5]:
+        assert val(cf, k) == cbind.horner(x, gsh * pow(w, k, R) % R), "coset forward, index %d" % k
+    del cf
+    inv = x.copy()
+    _lib.check(L.zkr_ntt(zctx, _lib.buf_ptr(inv), log_n, INV, 0))
+    for k in ks[:5]:
+        assert cbind.horner(inv, pow(w, k, R)) == val(x, k), "inverse, index %d" % k
+
+
+def test_fill_geometric_closed_form(zctx):
+    """zkr_fill_geometric (the dense NTT workload whose transform bench.py checks in closed form):
+    x_j = c g^j, and NTT(x)[k] = c (g^N - 1) / (g w^k - 1)."""
+    L = _lib.lib()
+    log_n = 14
+    n = 1 << log_n
+    c, gg = 0x1234567890ABCDEF1234567890ABCDEF % R, 0xFEDCBA9876543210FEDCBA987654321 % R
+    d = C.c_void_p()
+    _lib.check(L.zkr_dev_malloc(zctx, n * 32, C.byref(d)))
+    _lib.check(L.zkr_fill_geometric(zctx, d, n, _lib.buf_ptr(pack([c])), _lib.buf_ptr(pack([gg])), 0, log_n, 1, 0))
+    out = np.zeros(n * 32, dtype=np.uint8)
+    _lib.check(L.zkr_dev_download(zctx, _lib.buf_ptr(out), d, n * 32))
+    assert unpack(out) == [c * pow(gg, j, R) % R for j in range(n)]
+    _lib.check(L.zkr_ntt(zctx, d, log_n, FWD, 1))
+    _lib.check(L.zkr_dev_download(zctx, _lib.buf_ptr(out), d, n * 32))
+    w = g.root_of_unity(log_n)
+    top = c * (pow(gg, n, R) - 1) % R
+    got = unpack(out)
+    for k in (0, 1, 77, n - 1):
+        assert got[k] == top * pow((gg * pow(w, k, R) - 1) % R, -1, R) % R
+    assert got == g.ntt([c * pow(gg, j, R) % R for j in range(n)])
+    _lib.check(L.zkr_dev_free(zctx, d))

@@ -209,10 +209,13 @@ def test_prove_batch_round_robin(gp):
         gp2.close()
 
 
-@pytest.mark.parametrize("shape", ["withdraw", "tx", "tx_2p20"])
+@pytest.mark.parametrize("shape", ["withdraw", "tx", "tx_2p20", "tx_2p22"])
 def test_prove_full_size(gp, shape):
-    """BASELINE configs[0..1] at full size: GPU setup -> prove -> toxic-waste exponent check (no MSM / NTT
-    code shared with the GPU path) -> pairing verification -> tamper-negative -> determinism."""
+    """BASELINE configs[0..1] and the per-GPU unit of configs[4] at full size: GPU setup -> prove -> toxic-waste
+    exponent check (no MSM / NTT code shared with the GPU path) -> pairing verification -> tamper-negative ->
+    determinism.  The exponent sums are independent of (r, s) and computed once per circuit: on Python ints up to the
+    tx.circom size, by their C restatement above it (held equal at the tx.circom size here and in tests/test_oracle_c.py)."""
+    from oracle import cbind
     nc, npub = synth.SHAPES[shape]
     t0 = time.time()
     r1, w = synth.generate(nc, npub, seed=11)
@@ -228,13 +231,21 @@ def test_prove_full_size(gp, shape):
     print("\n%s: m=2^%d nVars=%d prove %.2f ms (setup+gen %.1f s) stats=%s" % (
         shape, m.bit_length() - 1, r1.nVars, stats["total_ms"], time.time() - t0, stats))
     proof = g.proof_from_bytes(got)
-    assert g.exponent_check_flat(r1.with_input_rows(), r1.pool, npub, w, TOXIC, m, proof, r, s)
+    mats = r1.with_input_rows()
+    sums = cbind.exponent_sums(mats, r1.pool, npub, wbin, TOXIC[0], m)
+    if shape in ("withdraw", "tx"):
+        assert sums == g.exponent_sums_flat(mats, r1.pool, npub, w, TOXIC, m)
+    assert g.exponent_check_flat(mats, r1.pool, npub, w, TOXIC, m, proof, r, s, sums=sums)
     pub = w[1:npub + 1]
-    assert g.verify(vk, proof, pub)
     bad = list(pub)
     bad[-1] = (bad[-1] + 1) % R
-    assert not g.verify(vk, proof, bad)
+    if shape != "tx_2p22":                       # the Python pairing verifier's vk_x loop is per public input
+        assert g.verify(vk, proof, pub)
+        assert not g.verify(vk, proof, bad)
+    vkey = gp.load_vkey(vk["bin"])               # the library's verifier (GPU vk_x MSM + host pairing product)
+    assert gp.verify(vkey, got, pub)
+    assert not gp.verify(vkey, got, bad)
     zero, _ = gp.prove(key, wbin, 0, 0)          # snarkjs debug mode
-    assert g.exponent_check_flat(r1.with_input_rows(), r1.pool, npub, w, TOXIC, m, g.proof_from_bytes(zero), 0, 0)
+    assert g.exponent_check_flat(mats, r1.pool, npub, w, TOXIC, m, g.proof_from_bytes(zero), 0, 0, sums=sums)
     gp.L.zkr_pkey_free(key)
     gp._keys.remove(key)

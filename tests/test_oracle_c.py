@@ -65,3 +65,35 @@ def test_c_ntt_modes():
         for mode in (0, 1):
             assert unpack(cbind.ntt(pack(x), bits, False, False, mode, 4)) == g.ntt(x)
             assert unpack(cbind.ntt(pack(x), bits, True, True, mode, 4)) == g.coset_intt(x, sh)
+
+
+@pytest.mark.parametrize("group", [1, 2])
+def test_c_ap_points_equal_fixed_base(group):
+    """oracle_ap_points (the host-side generator of the 2^20 arithmetic-progression MSM check) against per-point
+    fixed-base multiplication on Python ints, including a step that walks through the point at infinity."""
+    from helpers import unpack_g1, unpack_g2
+    fb = bn.fixed_base(group)
+    a0, d, n = 0x1234567, R - 3, 400
+    base, step = fb.mul_many([a0, d])
+    enc = (lambda pt: pack_g1([pt]).tobytes()) if group == 1 else (lambda pt: pack_g2([pt]).tobytes())
+    got = cbind.ap_points(group, enc(base), enc(step), n)
+    want = fb.mul_many([(a0 + i * d) % R for i in range(n)])
+    assert (unpack_g1(got) if group == 1 else unpack_g2(got)) == want
+    # (R - 2) G + i * G passes through infinity at i = 2 and through P == Q at i = 3
+    base, step = fb.mul_many([R - 2, 1])
+    got = cbind.ap_points(group, enc(base), enc(step), 6)
+    want = fb.mul_many([(R - 2 + i) % R for i in range(6)])
+    assert want[2] is None and (unpack_g1(got) if group == 1 else unpack_g2(got)) == want
+
+
+def test_c_horner_and_exponent_sums():
+    rng = random.Random(11)
+    c = [0, R - 1] + [rng.randrange(R) for _ in range(300)]
+    for x in (0, 1, R - 1, rng.randrange(R)):
+        assert cbind.horner(pack(c), x) == sum(v * pow(x, j, R) for j, v in enumerate(c)) % R
+    toxic = (0x1234567890ABCDEF1234567, 222222222222223, 3333333333333331, 44444444444447, 5555555555555557)
+    for nc, npub in ((5, 1), (700, 5), (3000, 17)):
+        r1, w = synth.generate(nc, npub, seed=nc)
+        _, m = r1.domain()
+        want = g.exponent_sums_flat(r1.with_input_rows(), r1.pool, npub, w, toxic, m)
+        assert cbind.exponent_sums(r1.with_input_rows(), r1.pool, npub, synth.witness_bytes(w), toxic[0], m) == want
