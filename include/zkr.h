@@ -314,7 +314,7 @@ int zkr_synth_points(zkr_ctx* ctx, int group, const void* scalars, size_t n, voi
  * a, b, out: n x 32 B host buffers (Montgomery form operands for mul/add/sub/sqr/inverse). */
 int zkr_test_field_op(zkr_ctx* ctx, int field, int op, const void* a, const void* b, void* out, size_t n);
 /* group 1/2.  op: 0 = affine+affine (via XYZZ mixed add), 1 = double, 2 = scalar mul by k[i] (32 B std),
- * 3 = xyzz full add of (P+P) and Q (exercises add()).  Points: affine Montgomery, x == 0 = infinity;
+ * 3 = 2P + 2Q through the full XYZZ add (both operands with non-trivial zz).  Points: affine Montgomery, x == 0 = infinity;
  * out affine Montgomery. */
 int zkr_test_curve_op(zkr_ctx* ctx, int group, int op, const void* p, const void* q_or_k, void* out, size_t n);
 /* white-box: copy an internal MSM work buffer of `b` to the host (what: 0 table, 1/2 keys, 3/4 vals,

@@ -118,11 +118,15 @@ static __global__ void k_digits(const uint32_t* __restrict__ scalars, const uint
 
 // ------------------------------------------------------------------------------------------------
 // level 1: affine table entries -> bucket sums / boundary partials
+// It also records where every bucket's run begins and ends in the sorted list (run_lo / run_hi, null = off): the thread
+// that sees a key change owns that boundary; the boundary at a chunk's first entry is found by reading the previous
+// chunk's last key.  k_bucket_gather turns the head / tail partials into bucket sums with these bounds in ONE launch.
 template <class F, bool PREFETCH>
-__global__ void __launch_bounds__(kAccumThreads)
+__global__ void __launch_bounds__(kAccumThreads, sizeof(F) == 32 ? 4 : 2)       // G1: 128 registers, 4 CTAs / SM
 k_accum_affine(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint32_t total, int logL,
                const char* __restrict__ table, XYZZ<F>* __restrict__ buckets, XYZZ<F>* __restrict__ bnd,
-               uint32_t* __restrict__ bnd_keys, uint32_t sentinel) {
+               uint32_t* __restrict__ bnd_keys, uint32_t sentinel, uint32_t* __restrict__ run_lo) {
+    uint32_t* const run_hi = run_lo + sentinel;      // one allocation: [lo of every bucket | hi of every bucket]
     extern __shared__ uint32_t sm[];
     constexpr size_t AB = 2 * sizeof(F);
     const int L = 1 << logL, LP = L + 1;
@@ -153,8 +157,17 @@ k_accum_affine(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ v
     uint32_t head_key = sentinel, tail_key = sentinel;
     Affine<F> nxt;
     bool have = cur < sentinel;
+    const uint32_t p0 = (uint32_t)t << logL;         // sorted position of this chunk's first entry (< 2^31 + padding)
+    if (run_lo && p0 <= total) {
+        const uint32_t prevk = (p0 > 0) ? keys[p0 - 1] : sentinel;
+        if (p0 == 0 || prevk != cur) {
+            if (have) run_lo[cur] = p0;
+            if (p0 > 0 && prevk < sentinel) run_hi[prevk] = p0;
+        }
+    }
     if (PREFETCH && have) nxt = Affine<F>::load_ro(table + AB * (size_t)(mv[0] & ~kNegBit));
-    for (int j = 0; j < L; j++) {
+    int j = 0;                                       // after the loop: the chunk's first unprocessed entry (a sentinel) or L
+    for (; j < L; j++) {
         if (!have) break;
         const uint32_t key = mk[j], v = mv[j];
         Affine<F> p;
@@ -163,6 +176,10 @@ k_accum_affine(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ v
         have = (j + 1 < L) && (mk[j + 1] < sentinel);
         if (PREFETCH && have) nxt = Affine<F>::load_ro(table + AB * (size_t)(mv[j + 1] & ~kNegBit));
         if (key != cur) {
+            if (run_lo) {
+                run_hi[cur] = p0 + j;
+                run_lo[key] = p0 + j;
+            }
             if (first_run) {
                 acc.store(bnd + 2 * t);
                 head_key = cur;
@@ -184,9 +201,91 @@ k_accum_affine(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ v
             acc.store(bnd + 2 * t + 1);
             tail_key = cur;
         }
+        if (run_lo) {
+            // the run's end, if it lies in this chunk: a sentinel follows, or the list ends at / before the chunk's end
+            // (the boundary at the next chunk's first entry belongs to that chunk's thread)
+            if (j < L) run_hi[cur] = p0 + j;
+            else if (p0 + L >= total) run_hi[cur] = total;
+        }
     }
-    bnd_keys[2 * t] = head_key;
-    bnd_keys[2 * t + 1] = tail_key;
+    if (bnd_keys) {
+        bnd_keys[2 * t] = head_key;
+        bnd_keys[2 * t + 1] = tail_key;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Boundary partials -> bucket sums in ONE launch (replaces the recursive boundary levels + k_accum_finish: up to 7
+// launches of shrinking, latency-bound work per MSM).  Bucket b's entries are the sorted positions [lo, hi); level-1
+// thread t owns [t L, (t+1) L).  The partial sums of b are therefore
+//     thread t0 = lo / L : its HEAD slot if the run starts the chunk, else its TAIL slot -- unless the run lies strictly
+//                          inside the chunk, in which case level 1 has already stored the complete bucket;
+//     threads t0+1 .. t1 = (hi-1) / L : their HEAD slots (the run starts their chunk).
+// One thread per bucket adds them (about run length / L + 1 additions: ~7 at 2^20); buckets with more than kHeavyRun
+// partials (the {0, 1} witness skew, adversarial scalar sets) go to a list that k_bucket_gather_heavy sums with one
+// CTA per bucket.
+constexpr int kGatherThreads = 64;
+constexpr uint32_t kHeavyRun = 48;
+constexpr uint32_t kNoRun = 0xffffffffu;
+constexpr int kHeavyThreads = 128;
+constexpr int kHeavyBlocks = 64;
+
+template <class F>
+__global__ void __launch_bounds__(kGatherThreads)
+k_bucket_gather(const uint32_t* __restrict__ keys, uint32_t total, int logL, const uint32_t* __restrict__ run_lo,
+                const uint32_t* __restrict__ run_hi, const XYZZ<F>* __restrict__ bnd, XYZZ<F>* __restrict__ buckets,
+                uint32_t nbuckets, uint32_t* __restrict__ heavy, uint32_t* __restrict__ n_heavy) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbuckets) return;
+    const uint32_t lo = run_lo[b];
+    if (lo == kNoRun) return;                         // empty bucket: stays the identity (memset)
+    const uint32_t hi = run_hi[b];
+    const uint32_t t0 = lo >> logL, t1 = (hi - 1) >> logL;
+    const bool aligned = lo == (t0 << logL);
+    if (t0 == t1) {
+        // one chunk: head slot, tail slot (run reaches the chunk's end or the end of the real entries), or already complete
+        const bool to_end = hi >= ((t0 + 1) << logL) || hi >= total || keys[hi] >= nbuckets;
+        if (aligned) XYZZ<F>::load(bnd + 2 * (size_t)t0).store(buckets + b);
+        else if (to_end) XYZZ<F>::load(bnd + 2 * (size_t)t0 + 1).store(buckets + b);
+        return;
+    }
+    if (t1 - t0 + 1 > kHeavyRun) {
+        heavy[atomicAdd(n_heavy, 1u)] = b;
+        return;
+    }
+    XYZZ<F> acc = XYZZ<F>::load(bnd + 2 * (size_t)t0 + (aligned ? 0 : 1));
+#pragma unroll 1
+    for (uint32_t t = t0 + 1; t <= t1; t++) acc.add(XYZZ<F>::load(bnd + 2 * (size_t)t));
+    acc.store(buckets + b);
+}
+
+// one CTA per heavy bucket (grid-stride over the list): strided partial sums per thread, then a tree in shared memory
+template <class F>
+__global__ void __launch_bounds__(kHeavyThreads)
+k_bucket_gather_heavy(int logL, const uint32_t* __restrict__ run_lo, const uint32_t* __restrict__ run_hi,
+                      const XYZZ<F>* __restrict__ bnd, XYZZ<F>* __restrict__ buckets, const uint32_t* __restrict__ heavy,
+                      const uint32_t* __restrict__ n_heavy) {
+    extern __shared__ unsigned char smraw[];
+    XYZZ<F>* sp = reinterpret_cast<XYZZ<F>*>(smraw);
+    const uint32_t n = *n_heavy;
+    for (uint32_t h = blockIdx.x; h < n; h += gridDim.x) {
+        const uint32_t b = heavy[h];
+        const uint32_t lo = run_lo[b], hi = run_hi[b];
+        const uint32_t t0 = lo >> logL, t1 = (hi - 1) >> logL;
+        const bool aligned = lo == (t0 << logL);
+        XYZZ<F> acc = XYZZ<F>::identity();
+#pragma unroll 1
+        for (uint32_t t = t0 + threadIdx.x; t <= t1; t += kHeavyThreads)
+            acc.add(XYZZ<F>::load(bnd + 2 * (size_t)t + ((t == t0 && !aligned) ? 1 : 0)));
+        sp[threadIdx.x] = acc;
+        __syncthreads();
+        for (int d = kHeavyThreads / 2; d >= 1; d >>= 1) {
+            if ((int)threadIdx.x < d) xyzz_add_mem(&sp[threadIdx.x], &sp[threadIdx.x], &sp[threadIdx.x + d]);
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) sp[0].store(buckets + b);
+        __syncthreads();
+    }
 }
 
 // level >= 2: XYZZ partials (with sentinel holes) -> bucket sums / boundary partials
@@ -452,8 +551,24 @@ struct MsmWork {                      // per-bases device work buffers
     void* red = nullptr;              // 2^lr + 2^lc row / column sums, then lr + lc + 1 weighted terms
     unsigned int* red_counter = nullptr;
     void* result = nullptr;           // 1 XYZZ
+    uint32_t *run_lo = nullptr, *run_hi = nullptr;     // per bucket: [lo, hi) of its run in the sorted list (kNoRun = empty)
+    uint32_t *heavy = nullptr, *n_heavy = nullptr;     // buckets whose partials one CTA sums (k_bucket_gather_heavy)
     int* range_err = nullptr;
     size_t bytes = 0;
+    // where the last radix sort left the sorted (bucket, point-ref) pairs: read by a second base set that shares them
+    mutable const uint32_t* sorted_keys = nullptr;
+    mutable const uint32_t* sorted_vals = nullptr;
+};
+
+// Optional hooks of one msm_run call (prover.cu).
+//   sorted_from : skip digit extraction and the radix sort and consume the sorted pairs another base set (same
+//                 scalars, same compaction map, same window plan: pi_b's B2' for B1') produced in this proof; the
+//                 caller has made `st` wait for that set's ev_sorted.
+//   ev_sorted   : recorded on st once the sorted pairs are final.
+//   ev_accum    : recorded on st after the level-1 accumulation (the bulk of the MSM) has been queued.
+struct MsmHooks {
+    const zkr_bases* sorted_from = nullptr;
+    cudaEvent_t ev_sorted = nullptr, ev_accum = nullptr;
 };
 
 }  // namespace zkr
@@ -470,6 +585,7 @@ struct zkr_bases {
     size_t bytes = 0;
     int logL = 5;
     uint32_t T1p = 0;                 // level-1 threads (padded to whole blocks)
+    uint64_t map_hash = 0;            // FNV-1a of the compact -> scalar index map (equal maps <=> shareable sort)
 };
 
 namespace zkr {
@@ -480,7 +596,8 @@ template <class F>
 int bases_build(zkr_ctx* ctx, zkr_bases* b, const char* h_points, size_t n_src, int c_forced, cudaStream_t st,
                 const uint32_t* h_scalar_idx = nullptr);
 template <class F>
-int msm_run(zkr_ctx* ctx, cudaStream_t st, const zkr_bases* b, const uint32_t* d_scalars, XYZZ<F>* d_out);
+int msm_run(zkr_ctx* ctx, cudaStream_t st, const zkr_bases* b, const uint32_t* d_scalars, XYZZ<F>* d_out,
+            const MsmHooks* hooks = nullptr);
 void bases_release(zkr_bases* b);
 
 // ---------------------------------------------------------------- implementation (header-only, two TUs)
@@ -502,6 +619,14 @@ int bases_build(zkr_ctx* ctx, zkr_bases* b, const char* h_points, size_t n_src, 
     }
     b->n = (uint32_t)idx.size();
     const uint32_t n = b->n;
+    {
+        uint64_t h = 1469598103934665603ull;
+        for (uint32_t k = 0; k < n; k++) {
+            const uint32_t v = h_scalar_idx ? h_scalar_idx[idx[k]] : idx[k];
+            for (int sft = 0; sft < 32; sft += 8) h = (h ^ ((v >> sft) & 0xff)) * 1099511628211ull;
+        }
+        b->map_hash = h;
+    }
     b->plan = MsmPlan::choose(n ? n : 1, c_forced);
     const int W = b->plan.W;
     if ((uint64_t)W * n >= (1ull << 31)) {
@@ -562,6 +687,11 @@ int bases_build(zkr_ctx* ctx, zkr_bases* b, const char* h_points, size_t n_src, 
     ZKR_CUDA(cudaMalloc(&wk.red_counter, sizeof(unsigned int)));
     ZKR_CUDA(cudaMemsetAsync(wk.red_counter, 0, sizeof(unsigned int), st));
     ZKR_CUDA(cudaMalloc(&wk.result, XB));
+    ZKR_CUDA(cudaMalloc(&wk.run_lo, 8 * (size_t)b->plan.nbuckets));
+    wk.run_hi = wk.run_lo + b->plan.nbuckets;
+    ZKR_CUDA(cudaMalloc(&wk.heavy, 4 * (size_t)b->plan.nbuckets));
+    ZKR_CUDA(cudaMalloc(&wk.n_heavy, 4));
+    wk.bytes += 12 * (size_t)b->plan.nbuckets + 4;
     ZKR_CUDA(cudaMalloc(&wk.range_err, sizeof(int)));
     ZKR_CUDA(cudaMemsetAsync(wk.range_err, 0, sizeof(int), st));
     wk.bytes += wk.cub_bytes + XB * ((size_t)b->plan.nbuckets + bnd0 + bnd1 + nred + 1) + 4 * (bnd0 + bnd1);
@@ -572,12 +702,14 @@ int bases_build(zkr_ctx* ctx, zkr_bases* b, const char* h_points, size_t n_src, 
     ZKR_CUDA(cudaFuncSetAttribute(k_bucket_weighted<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(XB * kReduceThreads)));
     ZKR_CUDA(cudaFuncSetAttribute((k_accum_affine<F, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
     ZKR_CUDA(cudaFuncSetAttribute((k_accum_affine<F, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+    ZKR_CUDA(cudaFuncSetAttribute(k_bucket_gather_heavy<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(XB * kHeavyThreads)));
     ZKR_CUDA(cudaStreamSynchronize(st));
     return ZKR_OK;
 }
 
 template <class F>
-int msm_run(zkr_ctx* ctx, cudaStream_t st, const zkr_bases* b, const uint32_t* d_scalars, XYZZ<F>* d_out) {
+int msm_run(zkr_ctx* ctx, cudaStream_t st, const zkr_bases* b, const uint32_t* d_scalars, XYZZ<F>* d_out,
+            const MsmHooks* hooks) {
     constexpr size_t XB = 4 * sizeof(F);
     constexpr bool kPrefetch = sizeof(F) == 32;    // G2 is register-bound; no software prefetch there
     const uint32_t n = b->n;
@@ -589,12 +721,26 @@ int msm_run(zkr_ctx* ctx, cudaStream_t st, const zkr_bases* b, const uint32_t* d
     const int c = b->plan.c, W = b->plan.W;
     const uint32_t nb = b->plan.nbuckets;
     const uint32_t total = (uint32_t)W * n;
-    ZKR_LAUNCH(ctx, k_digits, ceil_div(n, 128), 128, 0, st, d_scalars, b->src_index, n, c, W, nb, wk.keys[0],
-               wk.vals[0], wk.range_err);
-    cub::DoubleBuffer<uint32_t> dk(wk.keys[0], wk.keys[1]), dv(wk.vals[0], wk.vals[1]);
-    size_t tmp = wk.cub_bytes;
-    ZKR_CUDA(cub::DeviceRadixSort::SortPairs(wk.cub_tmp, tmp, dk, dv, (int)total, 0, c, st));
-    ctx->launches += 4;   // CUB: histogram + onesweep passes (not this library's own kernels, counted as a block)
+    const uint32_t *skeys, *svals;
+    if (hooks && hooks->sorted_from) {
+        const zkr_bases* o = hooks->sorted_from;
+        if (o->n != n || o->plan.c != c || o->map_hash != b->map_hash || !o->work.sorted_keys) {
+            set_error("msm_run: the base sets do not share a sort (different point maps or window plans)");
+            return ZKR_E_INVALID;
+        }
+        skeys = o->work.sorted_keys;
+        svals = o->work.sorted_vals;
+    } else {
+        ZKR_LAUNCH(ctx, k_digits, ceil_div(n, 128), 128, 0, st, d_scalars, b->src_index, n, c, W, nb, wk.keys[0],
+                   wk.vals[0], wk.range_err);
+        cub::DoubleBuffer<uint32_t> dk(wk.keys[0], wk.keys[1]), dv(wk.vals[0], wk.vals[1]);
+        size_t tmp = wk.cub_bytes;
+        ZKR_CUDA(cub::DeviceRadixSort::SortPairs(wk.cub_tmp, tmp, dk, dv, (int)total, 0, c, st));
+        ctx->launches += 4;   // CUB: histogram + onesweep passes (not this library's own kernels, counted as a block)
+        skeys = wk.sorted_keys = dk.Current();
+        svals = wk.sorted_vals = dv.Current();
+        if (hooks && hooks->ev_sorted) ZKR_CUDA(cudaEventRecord(hooks->ev_sorted, st));
+    }
     ZKR_CUDA(cudaMemsetAsync(wk.buckets, 0, XB * (size_t)nb, st));
 
     // level 1
@@ -602,13 +748,27 @@ int msm_run(zkr_ctx* ctx, cudaStream_t st, const zkr_bases* b, const uint32_t* d
     const size_t smem = (size_t)(kAccumThreads / 32) * 2 * 32 * (L + 1) * 4;
     XYZZ<F>* buckets = (XYZZ<F>*)wk.buckets;
     const int pslot = ctx->prof_begin(sizeof(F) == 32 ? PROF_ACCUM_G1 : PROF_ACCUM_G2, st, (double)total);
-    ZKR_LAUNCH(ctx, (k_accum_affine<F, kPrefetch>), b->T1p / kAccumThreads, kAccumThreads, smem, st, dk.Current(),
-               dv.Current(), total, b->logL, b->table, buckets, (XYZZ<F>*)wk.bnd[0], wk.bnd_keys[0], nb);
+    // ZKR_MSM_LEVELS=1: the round-1 recursive boundary levels instead of the one-launch gather (A/B knob)
+    static const bool use_levels = getenv("ZKR_MSM_LEVELS") && atoi(getenv("ZKR_MSM_LEVELS")) != 0;
+    if (!use_levels) {
+        ZKR_CUDA(cudaMemsetAsync(wk.run_lo, 0xff, 4 * (size_t)nb, st));
+        ZKR_CUDA(cudaMemsetAsync(wk.n_heavy, 0, 4, st));
+    }
+    ZKR_LAUNCH(ctx, (k_accum_affine<F, kPrefetch>), b->T1p / kAccumThreads, kAccumThreads, smem, st, skeys, svals, total,
+               b->logL, b->table, buckets, (XYZZ<F>*)wk.bnd[0], use_levels ? wk.bnd_keys[0] : nullptr, nb,
+               use_levels ? nullptr : wk.run_lo);
     ctx->prof_end(sizeof(F) == 32 ? PROF_ACCUM_G1 : PROF_ACCUM_G2, pslot, st);
-    // boundary levels
+    if (hooks && hooks->ev_accum) ZKR_CUDA(cudaEventRecord(hooks->ev_accum, st));
+    if (!use_levels) {
+        ZKR_LAUNCH(ctx, k_bucket_gather<F>, ceil_div(nb, kGatherThreads), kGatherThreads, 0, st, skeys, total, b->logL,
+                   wk.run_lo, wk.run_hi, (const XYZZ<F>*)wk.bnd[0], buckets, nb, wk.heavy, wk.n_heavy);
+        ZKR_LAUNCH(ctx, k_bucket_gather_heavy<F>, kHeavyBlocks, kHeavyThreads, XB * kHeavyThreads, st, b->logL, wk.run_lo,
+                   wk.run_hi, (const XYZZ<F>*)wk.bnd[0], buckets, wk.heavy, wk.n_heavy);
+    }
+    // boundary levels (round-1 path)
     size_t cnt = 2 * (size_t)b->T1p;
     int cur = 0;
-    for (;;) {
+    for (; use_levels;) {
         const int llog = level_log(cnt);
         const size_t lvl = (size_t)1 << llog;
         if (cnt <= kFinishMax) {

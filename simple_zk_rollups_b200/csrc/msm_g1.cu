@@ -2,7 +2,7 @@
 #include "msm.cuh"
 namespace zkr {
 template int bases_build<Fq>(zkr_ctx*, zkr_bases*, const char*, size_t, int, cudaStream_t, const uint32_t*);
-template int msm_run<Fq>(zkr_ctx*, cudaStream_t, const zkr_bases*, const uint32_t*, XYZZ<Fq>*);
+template int msm_run<Fq>(zkr_ctx*, cudaStream_t, const zkr_bases*, const uint32_t*, XYZZ<Fq>*, const MsmHooks*);
 int g1_result_to_affine_std(zkr_ctx* ctx, cudaStream_t st, const void* d_xyzz, void* d_out64) {
     ZKR_LAUNCH(ctx, k_xyzz_to_affine_std<Fq>, 1, 1, 0, st, (const XYZZ<Fq>*)d_xyzz, (char*)d_out64);
     return ZKR_OK;
@@ -16,6 +16,9 @@ int bases_group(const zkr_bases* b) { return b->group; }
 zkr_ctx* bases_ctx(const zkr_bases* b) { return b->ctx; }
 void bases_set_group(zkr_bases* b, int g) { b->group = g; }
 uint64_t bases_n_src(const zkr_bases* b) { return b->n_src; }
+bool bases_share_sort(const zkr_bases* a, const zkr_bases* b) {
+    return a && b && a->n && a->n == b->n && a->plan.c == b->plan.c && a->plan.W == b->plan.W && a->map_hash == b->map_hash;
+}
 void* bases_result_buf(const zkr_bases* b) { return b->work.result; }
 void bases_info(const zkr_bases* b, uint64_t* n, int* c, int* W, uint64_t* bytes) {
     if (n) *n = b->n;
@@ -27,8 +30,13 @@ int bases_build_g1(zkr_ctx* ctx, zkr_bases* b, const char* p, size_t n, int c, c
     b->ctx = ctx;
     return bases_build<Fq>(ctx, b, p, n, c, st, sidx);
 }
-int msm_run_g1(zkr_ctx* ctx, cudaStream_t st, const zkr_bases* b, const uint32_t* sc, void* out) {
-    return msm_run<Fq>(ctx, st, b, sc, (XYZZ<Fq>*)out);
+int msm_run_g1(zkr_ctx* ctx, cudaStream_t st, const zkr_bases* b, const uint32_t* sc, void* out, const zkr_bases* sorted_from,
+               cudaEvent_t ev_sorted, cudaEvent_t ev_accum) {
+    MsmHooks h;
+    h.sorted_from = sorted_from;
+    h.ev_sorted = ev_sorted;
+    h.ev_accum = ev_accum;
+    return msm_run<Fq>(ctx, st, b, sc, (XYZZ<Fq>*)out, &h);
 }
 int bases_range_error(const zkr_bases* b, cudaStream_t st, int* err) {
     *err = 0;
@@ -70,7 +78,8 @@ void bases_release(zkr_bases* b) {
     if (!b) return;
     MsmWork& w = b->work;
     void* ps[] = {b->src_index, b->table, w.keys[0], w.keys[1], w.vals[0], w.vals[1], w.cub_tmp, w.buckets,
-                  w.bnd[0], w.bnd[1], w.bnd_keys[0], w.bnd_keys[1], w.red, w.red_counter, w.result, w.range_err};
+                  w.bnd[0], w.bnd[1], w.bnd_keys[0], w.bnd_keys[1], w.red, w.red_counter, w.result, w.range_err,
+                  w.run_lo, w.heavy, w.n_heavy};
     for (void* p : ps) cudaFree(p);
     delete b;
 }

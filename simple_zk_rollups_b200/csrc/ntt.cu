@@ -76,6 +76,25 @@ __global__ void k_pow_table(Fr* out, unsigned count, const Fr* base, unsigned lo
     v.store(out + i);
 }
 
+// out[(row << s) + col] = omega^((col * rev_k(row)) << tw_shift): the inter-pass twiddles of one pass, in the layout of a chunk
+__global__ void k_twfull(Fr* out, int chunk_log, int k, int tw_shift, const Fr* lo, const Fr* hi, int lb) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >> chunk_log) return;
+    const int s = chunk_log - k;
+    const unsigned row = (unsigned)(idx >> s), col = (unsigned)(idx & (((size_t)1 << s) - 1));
+    const unsigned rev = __brev(row) >> (32 - k);
+    const unsigned X = (col * rev) << tw_shift;
+    (Fr::load_ro(lo + (X & ((1u << lb) - 1))) * Fr::load_ro(hi + (X >> lb))).store(out + idx);
+}
+
+// out[p] = lo[j & mask] * hi[j >> lb] at j = bitrev(p): a two-level power table spread out in bit-reversed order
+__global__ void k_pow_bitrev(Fr* out, int log_n, const Fr* lo, const Fr* hi, int lb) {
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >> log_n) return;
+    const unsigned j = __brev((unsigned)p) >> (32 - log_n);
+    (Fr::load_ro(lo + (j & ((1u << lb) - 1))) * Fr::load_ro(hi + (j >> lb))).store(out + p);
+}
+
 // out[p] = c * g^j(p), standard form; c, g standard form.  j(p) = start + p (world_log < 0) or the transform index of
 // local element p of rank's COLS slab (see k_scale_pow_sharded, layout 0).  Workload generator: a dense vector whose
 // transform has a closed form on the host, X[k] = c (g^N - 1) / (g w^k - 1)  (bench.py, tests).
@@ -103,10 +122,30 @@ __device__ __forceinline__ int slot_of(int e) { return e + (e >> 3); }
 //   3  in place on a COLS slab (last DIT pass)
 // On a COLS slab (modes 1, 3) ls_ = log2 of the row stride in memory (s0 - g) and ctw_ = global column of
 // this rank's first local column (twiddles use global coordinates); otherwise ls == s and ctw == 0.
+// Fused element-wise work (H pipeline: no separate sweeps over memory).  Runtime values, uniform per launch:
+//   ld_op  LD_PLAIN | LD_MUL2: element = src[pos] * in2[pos] (S = A_T.B_T and P = A.B are formed while the first pass of
+//          their transform loads its tile) | LD_TAB: element = data[pos] * tab[pos] (coset scaling g^j / N, table stored
+//          in the order of the data)
+//   st_op  ST_PLAIN | ST_HFINAL: out[pos] = in2[pos] * K - x * tab[pos]   (h = S K - P g^-j K, see h_pipeline)
+// twfull != null: the inter-pass twiddle omega_N'^(col * rev(row)) comes from ONE table laid out like a chunk of the
+// data (coalesced like the data itself, one modmul per element) instead of the product of two sqrt(N)-sized tables
+// (two modmuls per element).  pos = position in the whole vector (MODE 0 only).
+enum { LD_PLAIN = 0, LD_MUL2 = 1, LD_TAB = 2 };
+enum { ST_PLAIN = 0, ST_HFINAL = 1 };
+struct PassFuse {
+    const Fr* src;       // LD_MUL2: first operand (null = data)
+    const Fr* in2;       // LD_MUL2: second operand; ST_HFINAL: S
+    const Fr* tab;       // LD_TAB / ST_HFINAL: table indexed by position
+    const Fr* kconst;    // ST_HFINAL: K
+    Fr* out;             // ST_HFINAL: destination (null = data)
+    const Fr* twfull;    // full inter-pass twiddle table of this pass (null = two-level)
+    int ld_op, st_op;
+};
+
 template <bool DIT, int MODE>
 __global__ void __launch_bounds__(256, 2)
 k_ntt_pass(Fr* __restrict__ data, int k, int c, int s, int ls_, int chunk_log, unsigned ctw_, const Fr* __restrict__ W,
-           int kw, const Fr* __restrict__ tlo, const Fr* __restrict__ thi, int lb, int tw_shift, NttXchg xp) {
+           int kw, const Fr* __restrict__ tlo, const Fr* __restrict__ thi, int lb, int tw_shift, NttXchg xp, PassFuse fz) {
     extern __shared__ uint32_t sm[];
     constexpr bool kSlab = MODE == 1 || MODE == 3;
     const int ls = kSlab ? ls_ : s;
@@ -127,25 +166,41 @@ k_ntt_pass(Fr* __restrict__ data, int k, int c, int s, int ls_, int chunk_log, u
     // ---- global -> shared.  blockDim.x == tile / 8 (launch_pass), so every thread moves exactly 8 elements = 16
     // 16-byte units; the loads of a group are all issued before the first shared store (an un-unrolled loop exposed
     // one HBM latency per unit: 12 % of the pass in the round-1 ncu source view, profiles/r01_ncu_ntt_pass.md).
-    if (DIT && s > 0) {
-        // DIT applies the inter-pass twiddle omega_N'^(col * rev(row)) BEFORE its butterflies: do it on the way in,
-        // whole elements per thread, so the register stages below hold nothing but the 8 butterfly operands
-        // (with the twiddle inside the first stage ptxas spilled 272 B per thread).
+    const size_t qbase = q << chunk_log;      // position of the chunk in the whole vector (fused ops, MODE 0)
+    if ((DIT && s > 0) || fz.ld_op != LD_PLAIN) {
+        // Whole elements per thread.  DIT applies the inter-pass twiddle omega_N'^(col * rev(row)) BEFORE its butterflies:
+        // do it on the way in, so the register stages below hold nothing but the 8 butterfly operands (with the twiddle
+        // inside the first stage ptxas spilled 272 B per thread).  The fused load operations ride on the same path.
+        const Fr* src = fz.src ? fz.src + qbase : chunk;
 #pragma unroll 1
         for (int g = 0; g < 2; g++) {
             Fr v[4];
+            size_t off[4];
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const int e = tid + (g * 4 + i) * (tile >> 3);
-                v[i] = Fr::load(chunk + ((size_t)(e >> c) << ls) + cm + (e & cmask));
+                off[i] = ((size_t)(e >> c) << ls) + cm + (e & cmask);
+                v[i] = Fr::load(src + off[i]);
+            }
+            if (fz.ld_op == LD_MUL2) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) v[i] = v[i] * Fr::load(fz.in2 + qbase + off[i]);
+            } else if (fz.ld_op == LD_TAB) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) v[i] = v[i] * Fr::load_ro(fz.tab + qbase + off[i]);
             }
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const int e = tid + (g * 4 + i) * (tile >> 3);
-                const unsigned rev = __brev((unsigned)(e >> c)) >> (32 - k);
-                const unsigned X = ((c0 + (e & cmask)) * rev) << tw_shift;
-                const Fr t = Fr::load_ro(tlo + (X & lbmask)) * Fr::load_ro(thi + (X >> lb));
-                v[i] = v[i] * t;
+                if (DIT && s > 0) {
+                    if (fz.twfull) {
+                        v[i] = v[i] * Fr::load_ro(fz.twfull + ((size_t)(e >> c) << s) + c0 + (e & cmask));
+                    } else {
+                        const unsigned rev = __brev((unsigned)(e >> c)) >> (32 - k);
+                        const unsigned X = ((c0 + (e & cmask)) * rev) << tw_shift;
+                        v[i] = v[i] * (Fr::load_ro(tlo + (X & lbmask)) * Fr::load_ro(thi + (X >> lb)));
+                    }
+                }
                 uint32_t* d = sm + slot_of(e);
 #pragma unroll
                 for (int l = 0; l < 8; l++) d[l * plane] = v[i].v[l];
@@ -231,10 +286,13 @@ k_ntt_pass(Fr* __restrict__ data, int k, int c, int s, int ls_, int chunk_log, u
             for (int j = 0; j < 8; j++) {
                 int e = base + (j << lo);
                 unsigned rho = e >> c, col = e & cmask;
-                unsigned rev = __brev(rho) >> (32 - k);
-                unsigned X = ((c0 + col) * rev) << tw_shift;
-                Fr t = Fr::load_ro(tlo + (X & lbmask)) * Fr::load_ro(thi + (X >> lb));
-                x[j] = x[j] * t;
+                if (fz.twfull) {
+                    x[j] = x[j] * Fr::load_ro(fz.twfull + ((size_t)rho << s) + c0 + col);
+                } else {
+                    unsigned rev = __brev(rho) >> (32 - k);
+                    unsigned X = ((c0 + col) * rev) << tw_shift;
+                    x[j] = x[j] * (Fr::load_ro(tlo + (X & lbmask)) * Fr::load_ro(thi + (X >> lb)));
+                }
             }
         }
 #pragma unroll
@@ -248,6 +306,22 @@ k_ntt_pass(Fr* __restrict__ data, int k, int c, int s, int ls_, int chunk_log, u
     }
 
     // ---- shared -> global
+    if (MODE == 0 && fz.st_op == ST_HFINAL) {
+        // whole elements: out[pos] = S[pos] * K - x * tab[pos]
+        const Fr K = Fr::load_ro(fz.kconst);
+        Fr* outp = (fz.out ? fz.out : data) + qbase;
+#pragma unroll 2
+        for (int e = tid; e < tile; e += blockDim.x) {
+            const size_t off = ((size_t)(e >> c) << ls) + cm + (e & cmask);
+            Fr x;
+            const uint32_t* d = sm + slot_of(e);
+#pragma unroll
+            for (int l = 0; l < 8; l++) x.v[l] = d[l * plane];
+            const Fr v = Fr::load(fz.in2 + qbase + off) * K - x * Fr::load_ro(fz.tab + qbase + off);
+            v.store(outp + off);
+        }
+        return;
+    }
     for (int u = tid; u < 2 * tile; u += blockDim.x) {
         int e = u >> 1, half = u & 1;
         int row = e >> c, col = e & cmask;
@@ -369,6 +443,12 @@ void ntt_tables_free(NttTables* t) {
     Fr** ps[] = {&t->wsub_f, &t->wsub_i, &t->tw_lo_f, &t->tw_hi_f, &t->tw_lo_i, &t->tw_hi_i, &t->cs_lo,
                  &t->cs_hi, &t->cs_hi_n, &t->ci_lo, &t->ci_hi_n, &t->ci_hi_h};
     for (Fr** p : ps) cudaFree(*p);
+    for (int i = 0; i < 4; i++) {
+        cudaFree(t->twfull_f[i]);
+        cudaFree(t->twfull_i[i]);
+    }
+    cudaFree(t->cs_br);
+    cudaFree(t->hf_br);
     cudaFree(t->roots);
     delete t;
 }
@@ -439,7 +519,7 @@ struct PassGeom {
 
 template <int MODE>
 static int launch_pass(zkr_ctx* ctx, cudaStream_t st, const NttTables* t, Fr* data, const PassGeom& g, bool dit,
-                       bool inverse, const NttXchg& xp, double prof_units) {
+                       bool inverse, const NttXchg& xp, double prof_units, const PassFuse& fz = PassFuse{}) {
     const Fr* W = inverse ? t->wsub_i : t->wsub_f;
     const Fr* tlo = inverse ? t->tw_lo_i : t->tw_lo_f;
     const Fr* thi = inverse ? t->tw_hi_i : t->tw_hi_f;
@@ -450,10 +530,32 @@ static int launch_pass(zkr_ctx* ctx, cudaStream_t st, const NttTables* t, Fr* da
     const int pid = (MODE == 1 || MODE == 2) ? PROF_NTT_XCHG : PROF_NTT_PASS;
     const int pslot = ctx->prof_begin(pid, st, prof_units);
     if (dit) ZKR_LAUNCH(ctx, (k_ntt_pass<true, MODE == 1 ? 3 : MODE>), g.blocks, threads, smem, st, data, g.k, g.c, g.s,
-                        g.ls, g.chunk_log, g.ctw, W, t->kw, tlo, thi, t->lb, g.tw_shift, xp);
+                        g.ls, g.chunk_log, g.ctw, W, t->kw, tlo, thi, t->lb, g.tw_shift, xp, fz);
     else ZKR_LAUNCH(ctx, (k_ntt_pass<false, (MODE == 2 || MODE == 3) ? 0 : MODE>), g.blocks, threads, smem, st, data, g.k, g.c, g.s,
-                    g.ls, g.chunk_log, g.ctw, W, t->kw, tlo, thi, t->lb, g.tw_shift, xp);
+                    g.ls, g.chunk_log, g.ctw, W, t->kw, tlo, thi, t->lb, g.tw_shift, xp, fz);
     ctx->prof_end(pid, pslot, st);
+    return ZKR_OK;
+}
+
+// Full inter-pass twiddle tables are used up to this size (2 x N x 32 B per direction and pass boundary: 1 GB per
+// direction at 2^24); above it, and on the sharded paths, the two-level lookup stays.  ZKR_NTT_TWFULL_MAXLOG overrides
+// (0 = never: A/B against the round-1 kernel).
+static int twfull_maxlog() {
+    static const int v = getenv("ZKR_NTT_TWFULL_MAXLOG") ? atoi(getenv("ZKR_NTT_TWFULL_MAXLOG")) : 24;
+    return v;
+}
+
+// table of pass i (chunk_log, k) for one direction, built on first use (cold path; synchronises the stream once)
+static int get_twfull(zkr_ctx* ctx, cudaStream_t st, NttTables* t, int i, int chunk_log, int k, bool inverse, const Fr** out) {
+    Fr** slot = inverse ? &t->twfull_i[i] : &t->twfull_f[i];
+    if (!*slot) {
+        const size_t cnt = (size_t)1 << chunk_log;
+        ZKR_CUDA(cudaMalloc(slot, cnt * sizeof(Fr)));
+        t->bytes += cnt * sizeof(Fr);
+        ZKR_LAUNCH(ctx, k_twfull, ceil_div(cnt, 256), 256, 0, st, *slot, chunk_log, k, t->log_n - chunk_log,
+                   inverse ? t->tw_lo_i : t->tw_lo_f, inverse ? t->tw_hi_i : t->tw_hi_f, t->lb);
+    }
+    *out = *slot;
     return ZKR_OK;
 }
 
@@ -461,10 +563,14 @@ static int launch_pass(zkr_ctx* ctx, cudaStream_t st, const NttTables* t, Fr* da
 //   dit == false: natural in  -> bit-reversed out (DIF)
 //   dit == true : bit-reversed in -> natural out  (DIT)
 // inverse selects omega^-1; no 1/N scaling is applied here.
-int ntt_run(zkr_ctx* ctx, cudaStream_t st, Fr* data, int log_n, bool dit, bool inverse) {
+// first / last (nullable): fused element-wise work of the first executed pass's load (ld_op, src, in2, tab) and of the
+// last executed pass's store (st_op, in2, tab, kconst, out).
+static int ntt_run_ex(zkr_ctx* ctx, cudaStream_t st, Fr* data, int log_n, bool dit, bool inverse, const PassFuse* first,
+                      const PassFuse* last) {
     NttTables* t;
     ZKR_TRY(ntt_get_tables(ctx, log_n, &t));
     if (log_n < 3) {
+        if (first || last) return ZKR_E_UNSUPPORTED;
         ZKR_LAUNCH(ctx, k_ntt_tiny, 1, 1, 0, st, data, log_n, inverse ? &t->roots->wi : &t->roots->w, dit, !dit);
         return ZKR_OK;
     }
@@ -489,9 +595,28 @@ int ntt_run(zkr_ctx* ctx, cudaStream_t st, Fr* data, int log_n, bool dit, bool i
         g.ctw = 0;
         g.tw_shift = log_n - g.chunk_log;
         g.blocks = 1u << (log_n - g.k - g.c);
-        ZKR_TRY(launch_pass<0>(ctx, st, t, data, g, dit, inverse, none, (double)((size_t)1 << log_n)));
+        PassFuse fz = {};
+        if (first && step == 0) {
+            fz.ld_op = first->ld_op;
+            fz.src = first->src;
+            fz.in2 = first->in2;
+            fz.tab = first->tab;
+        }
+        if (last && step == np - 1) {
+            fz.st_op = last->st_op;
+            fz.in2 = last->in2;         // a single-pass transform never combines LD_MUL2 with ST_HFINAL's in2: see h_pipeline
+            fz.tab = last->tab;
+            fz.kconst = last->kconst;
+            fz.out = last->out;
+        }
+        if (g.s > 0 && log_n <= twfull_maxlog()) ZKR_TRY(get_twfull(ctx, st, t, i, g.chunk_log, g.k, inverse, &fz.twfull));
+        ZKR_TRY(launch_pass<0>(ctx, st, t, data, g, dit, inverse, none, (double)((size_t)1 << log_n), fz));
     }
     return ZKR_OK;
+}
+
+int ntt_run(zkr_ctx* ctx, cudaStream_t st, Fr* data, int log_n, bool dit, bool inverse) {
+    return ntt_run_ex(ctx, st, data, log_n, dit, inverse, nullptr, nullptr);
 }
 
 // Rows of the sharded four-step, 2^k0.  The passes after the exchange work on contiguous rows of 2^s0
@@ -600,11 +725,51 @@ int ntt_scale_const(zkr_ctx* ctx, cudaStream_t st, Fr* x, size_t n, const Fr* cs
 //   h_j = ((L+U)_j - (L-U)_j) / 2
 // Pointwise products of two data vectors pick up a factor 1/R (Montgomery); the final constants
 // carry R/(2m) so the output has the same form (standard or Montgomery) as the inputs.
+//
+// No element-wise sweep runs on its own (bit-reversed output, the prover's case): S and P are formed while the first
+// pass of their transform loads its tile (LD_MUL2), the coset scaling g^j / m is a table multiply in the load of the DIT
+// transforms' first pass (LD_TAB), and h is assembled in the store of the last pass (ST_HFINAL).  A single-pass transform
+// (m <= 2^11) would need both LD_MUL2's and ST_HFINAL's second operand in one launch: there P is formed by the sweep.
 int h_pipeline(zkr_ctx* ctx, cudaStream_t st, Fr* A, Fr* B, Fr* S, Fr* h, int log_m, bool bitrev_out) {
     NttTables* t;
     ZKR_TRY(ntt_get_tables(ctx, log_m, &t));
     const size_t m = (size_t)1 << log_m;
     const int blk = 128, grid = ceil_div(m, blk);
+    static const bool unfused = getenv("ZKR_H_UNFUSED") && atoi(getenv("ZKR_H_UNFUSED")) != 0;   // A/B knob: round-1 pipeline
+    if (log_m >= 3 && bitrev_out && !unfused) {
+        if (!t->cs_br) {      // cold path: the two position-ordered tables of this size
+            ZKR_CUDA(cudaMalloc(&t->cs_br, m * sizeof(Fr)));
+            ZKR_CUDA(cudaMalloc(&t->hf_br, m * sizeof(Fr)));
+            t->bytes += 2 * m * sizeof(Fr);
+            ZKR_LAUNCH(ctx, k_pow_bitrev, ceil_div(m, 256), 256, 0, st, t->cs_br, log_m, t->cs_lo, t->cs_hi_n, t->lb);
+            ZKR_LAUNCH(ctx, k_pow_bitrev, ceil_div(m, 256), 256, 0, st, t->hf_br, log_m, t->ci_lo, t->ci_hi_h, t->lb);
+        }
+        int ks[4];
+        const bool single = plan_passes(log_m, ks) == 1;
+        PassFuse mulAB = {};
+        mulAB.ld_op = LD_MUL2;
+        mulAB.src = A;
+        mulAB.in2 = B;
+        ZKR_TRY(ntt_run_ex(ctx, st, S, log_m, false, true, &mulAB, nullptr));     // S <- DIF^-1(A_T . B_T)
+        ZKR_TRY(ntt_run(ctx, st, A, log_m, false, true));
+        ZKR_TRY(ntt_run(ctx, st, B, log_m, false, true));
+        PassFuse coset = {};
+        coset.ld_op = LD_TAB;
+        coset.tab = t->cs_br;
+        ZKR_TRY(ntt_run_ex(ctx, st, A, log_m, true, false, &coset, nullptr));     // A, B on the coset g<omega>
+        ZKR_TRY(ntt_run_ex(ctx, st, B, log_m, true, false, &coset, nullptr));
+        PassFuse mulP = {}, fin = {};
+        mulP.ld_op = LD_MUL2;
+        mulP.in2 = B;
+        fin.st_op = ST_HFINAL;
+        fin.in2 = S;
+        fin.tab = t->hf_br;
+        fin.kconst = &t->roots->hconst;
+        fin.out = h;
+        if (single) ZKR_LAUNCH(ctx, k_pointwise_mul, grid, blk, 0, st, A, A, B, m);
+        ZKR_TRY(ntt_run_ex(ctx, st, A, log_m, false, true, single ? nullptr : &mulP, &fin));
+        return ZKR_OK;
+    }
     ZKR_LAUNCH(ctx, k_pointwise_mul, grid, blk, 0, st, S, A, B, m);
     ZKR_TRY(ntt_run(ctx, st, A, log_m, false, true));
     ZKR_TRY(ntt_run(ctx, st, B, log_m, false, true));

@@ -30,6 +30,11 @@ struct NttTables {
     Fr *tw_lo_f = nullptr, *tw_hi_f = nullptr, *tw_lo_i = nullptr, *tw_hi_i = nullptr;  // omega_N^{+-X}
     Fr *cs_lo = nullptr, *cs_hi = nullptr, *cs_hi_n = nullptr;            // g^j ; hi / hi * 1/N
     Fr *ci_lo = nullptr, *ci_hi_n = nullptr, *ci_hi_h = nullptr;          // g^-j ; hi * 1/N ; hi * R/(2N)
+    // Full-size tables, built on first use (ntt.cu): one modmul and one coalesced 32-byte read per element instead of
+    // the two modmuls of a two-level lookup.  twfull_x[i]: inter-pass twiddles omega^(col * rev(row)) of pass i (laid out
+    // like one chunk of that pass's data); cs_br / hf_br: the H pipeline's g^j / N and g^-j R/(2N) at j = bitrev(position).
+    Fr *twfull_f[4] = {nullptr, nullptr, nullptr, nullptr}, *twfull_i[4] = {nullptr, nullptr, nullptr, nullptr};
+    Fr *cs_br = nullptr, *hf_br = nullptr;
     size_t bytes = 0;
 };
 

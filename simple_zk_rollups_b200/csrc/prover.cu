@@ -48,6 +48,10 @@ struct zkr_pkey {
     Fr* wext2 = nullptr;
     cudaEvent_t ev_up[2] = {};
     cudaEvent_t ev[16] = {};
+    // B1' and B2' take the same scalars through the same compaction map and window plan (B1_i is the point at infinity
+    // exactly when B2_i is): one digit extraction + radix sort, done on pi_b's stream, serves both MSMs
+    bool share_b_sort = false;
+    cudaEvent_t ev_b2_sorted = nullptr, ev_b2_accum = nullptr;
     size_t bytes = 0;
 };
 
@@ -259,6 +263,8 @@ void pkey_release(zkr_pkey* pk) {
     if (pk->pinned) cudaFreeHost(pk->pinned);
     for (auto& e : pk->ev)
         if (e) cudaEventDestroy(e);
+    if (pk->ev_b2_sorted) cudaEventDestroy(pk->ev_b2_sorted);
+    if (pk->ev_b2_accum) cudaEventDestroy(pk->ev_b2_accum);
     zkr_bases* bs[] = {pk->A, pk->B1, pk->B2, pk->C, pk->H};
     for (zkr_bases* b : bs) bases_release(b);
     delete pk;
@@ -414,6 +420,12 @@ static int pkey_load(zkr_ctx* ctx, const void* vbuf, size_t len, int rank, int w
     }
     cudaMemsetAsync(pk->err, 0, sizeof(int), st);
     for (auto& e : pk->ev) cudaEventCreate(&e);
+    cudaEventCreateWithFlags(&pk->ev_b2_sorted, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&pk->ev_b2_accum, cudaEventDisableTiming);
+    {
+        const char* e = getenv("ZKR_SHARE_SORT");       // A/B knob; default on
+        pk->share_b_sort = bases_share_sort(pk->B1, pk->B2) && !(e && atoi(e) == 0);
+    }
     NttTables* t;
     PK_TRY(ntt_get_tables(ctx, pk->log_m, &t));
     zkr_bases* bs[] = {pk->A, pk->B1, pk->B2, pk->C, pk->H};
@@ -485,21 +497,37 @@ static int prove_enqueue(zkr_ctx* ctx, const zkr_pkey* pk, char* d_proof, bool t
         for (cudaStream_t o : others) ZKR_CUDA(cudaStreamWaitEvent(o, ctx->ev_join[0], 0));
     }
     // heaviest first: the G2 MSM costs ~3 G1 MSMs
+    // ZKR_DELAY (experiment knob): chains named in it (A, B = B1', C, H = the hExps MSM) start their MSM only once the
+    // G2 accumulation kernel is done, so that their bulk overlaps the G2 chain's latency-bound tail
+    static const char* delay = getenv("ZKR_DELAY") ? getenv("ZKR_DELAY") : "";
+    auto delayed = [&](char who, cudaStream_t s) -> int {
+        if (par && strchr(delay, who)) ZKR_CUDA(cudaStreamWaitEvent(s, pk->ev_b2_accum, 0));
+        return ZKR_OK;
+    };
     if (timed) cudaEventRecord(ev[6], sB2);
-    ZKR_TRY(msm_run_g2(ctx, sB2, pk->B2, w, pk->res + R_B2));
+    ZKR_TRY(msm_run_g2(ctx, sB2, pk->B2, w, pk->res + R_B2, nullptr, pk->ev_b2_sorted, pk->ev_b2_accum));
     if (timed) cudaEventRecord(ev[7], sB2);
     // H chain
     if (!(h_first && par)) ZKR_TRY(h_front());
+    ZKR_TRY(delayed('H', sH));
     ZKR_TRY(msm_run_g1(ctx, sH, pk->H, (const uint32_t*)(pk->h + pk->h_lo), pk->res + R_H));
     if (timed) cudaEventRecord(ev[3], sH);
     // A, then s * pi_a
     if (timed) cudaEventRecord(ev[4], sA);
+    ZKR_TRY(delayed('A', sA));
     ZKR_TRY(msm_run_g1(ctx, sA, pk->A, w, pk->res + R_A));
     if (timed) cudaEventRecord(ev[5], sA);
     if (timed) cudaEventRecord(ev[8], sB1);
-    ZKR_TRY(msm_run_g1(ctx, sB1, pk->B1, w, pk->res + R_B1));
+    ZKR_TRY(delayed('B', sB1));
+    if (pk->share_b_sort) {
+        ZKR_CUDA(cudaStreamWaitEvent(sB1, pk->ev_b2_sorted, 0));
+        ZKR_TRY(msm_run_g1(ctx, sB1, pk->B1, w, pk->res + R_B1, pk->B2));
+    } else {
+        ZKR_TRY(msm_run_g1(ctx, sB1, pk->B1, w, pk->res + R_B1));
+    }
     if (timed) cudaEventRecord(ev[9], sB1);
     if (timed) cudaEventRecord(ev[10], sC);
+    ZKR_TRY(delayed('C', sC));
     ZKR_TRY(msm_run_g1(ctx, sC, pk->C, w, pk->res + R_C));
     if (timed) cudaEventRecord(ev[11], sC);
     if (comm && comm->world > 1) {

@@ -136,7 +136,8 @@ def test_fill_geometric_closed_form(zctx):
     c, gg = 0x1234567890ABCDEF1234567890ABCDEF % R, 0xFEDCBA9876543210FEDCBA987654321 % R
     d = C.c_void_p()
     _lib.check(L.zkr_dev_malloc(zctx, n * 32, C.byref(d)))
-    _lib.check(L.zkr_fill_geometric(zctx, d, n, _lib.buf_ptr(pack([c])), _lib.buf_ptr(pack([gg])), 0, log_n, 1, 0))
+    cb, gb = pack([c]), pack([gg])                 # named: buf_ptr does not keep its argument alive
+    _lib.check(L.zkr_fill_geometric(zctx, d, n, _lib.buf_ptr(cb), _lib.buf_ptr(gb), 0, log_n, 1, 0))
     out = np.zeros(n * 32, dtype=np.uint8)
     _lib.check(L.zkr_dev_download(zctx, _lib.buf_ptr(out), d, n * 32))
     assert unpack(out) == [c * pow(gg, j, R) % R for j in range(n)]
