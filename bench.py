@@ -715,6 +715,198 @@ def sharded_blocks(env, args, key_rank0):
     return res
 
 
+def run_sweep(args):
+    """BASELINE.json configs[2..3] on one B200 with the CPU path beside every row: G1 / G2 MSM 2^16 .. 2^26 (G2 .. 2^24) and
+    Fr NTT 2^16 .. 2^26, kernel-only with inputs resident in HBM (CUDA events, best of 5).  cpu_baseline per row
+    (this is bench.py's cpu_baseline leg: the only place that may execute oracle/): CPU-B = the C port's Pippenger /
+    iterative NTT on all host threads up to 2^22, CPU-A = its snarkjs-structured arithmetic (one double-and-add per
+    point, recursive radix-2 FFT) on one thread up to 2^16 (MSM) / 2^20 (NTT).  Checks: every MSM result == (sum k_i s_i
+    mod r) G with the sum (numpy) and the scalar multiplication (Python ints) on the host -- for the uniform, the
+    rollup-like and every adversarial scalar set of SURVEY 8(d) config 3 (iii); every NTT on x_j = c g^j against the
+    closed form at 8 random + first + last indices, plus the round trip."""
+    import numpy as np
+    import torch
+    from oracle import cbind
+    from simple_zk_rollups_b200 import _lib, prover
+    L = _lib.lib()
+    gp = prover.Groth16Prover(0)
+    ctx = gp.ctx
+    stream = torch.cuda.current_stream()
+    _lib.check(L.zkr_ctx_set_stream(ctx, C.c_void_p(stream.cuda_stream)))
+    cores = os.cpu_count() or 1
+    imad_peak, modmul_peak, ms_mb = C.c_double(), C.c_double(), C.c_float()
+    _lib.check(L.zkr_microbench(ctx, 0, 100000, C.byref(imad_peak), C.byref(ms_mb)))
+    _lib.check(L.zkr_microbench(ctx, 2, 20000, C.byref(modmul_peak), C.byref(ms_mb)))
+    res = {"what": "bench.py --sweep (one B200)", "imad_peak_per_s": imad_peak.value, "modmul_peak_per_s": modmul_peak.value,
+           "host_threads": cores, "msm": [], "ntt": []}
+    rng = np.random.default_rng(2026)
+
+    def timeit(fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            fn()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return min(ts), float(np.median(ts))
+
+    def w_model(n):
+        return min(-(-255 // c) * 10.0 * n + 28.0 * (1 << (c - 1)) for c in range(4, 24))
+
+    def wall(fn):
+        t0 = time.time()
+        fn()
+        return time.time() - t0
+
+    def host_g2_check(out, e):                     # G2 expectation: one fixed-base multiplication on the GPU (other kernel)
+        esc = np.frombuffer(int(e).to_bytes(32, "little"), dtype=np.uint8).copy()
+        exp_m = np.empty(128, dtype=np.uint8)
+        _lib.check(L.zkr_synth_points(ctx, 2, _lib.buf_ptr(esc), 1, _lib.buf_ptr(exp_m)))
+        rinv = pow(1 << 256, -1, Q_FIELD)
+        exp = b"".join((int.from_bytes(exp_m[i:i + 32].tobytes(), "little") * rinv % Q_FIELD).to_bytes(32, "little")
+                       for i in range(0, 128, 32))
+        return exp == out
+
+    for group, lo_log, hi_log in ((1, 16, args.sweep_max_log), (2, 16, min(24, args.sweep_max_log))):
+        if "msm" not in args.sweep:
+            break
+        for lg in range(lo_log, hi_log + 1, 2):
+            n = 1 << lg
+            t0 = time.time()
+            s64 = rng.integers(1, 1 << 63, size=n, dtype=np.uint64)
+            sc_pts = np.zeros((n, 32), dtype=np.uint8)
+            sc_pts[:, :8] = s64.view(np.uint8).reshape(n, 8)
+            ab = 64 if group == 1 else 128
+            pts = np.empty(n * ab, dtype=np.uint8)
+            _lib.check(L.zkr_synth_points(ctx, group, _lib.buf_ptr(sc_pts), n, _lib.buf_ptr(pts)))
+            bases = C.c_void_p()
+            _lib.check(L.zkr_bases_load(ctx, group, _lib.buf_ptr(pts), n, 0, C.byref(bases)))
+            cc, ww, nbytes = C.c_int(), C.c_int(), C.c_uint64()
+            _lib.check(L.zkr_bases_info(bases, None, C.byref(cc), C.byref(ww), C.byref(nbytes)))
+            t_load = time.time() - t0
+            ssum = int((s64 & np.uint64(0xFFFFFFFF)).sum(dtype=np.uint64)) + (int((s64 >> np.uint64(32)).sum(dtype=np.uint64)) << 32)
+            uni = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+            uni[:, 31] &= 0x1F
+            roll = uni.copy()
+            sel = rng.random(n) < 0.03
+            roll[sel] = 0
+            roll[sel, 0] = rng.integers(0, 2, size=int(sel.sum()), dtype=np.uint8)
+            const = lambda k: np.tile(np.frombuffer(int(k).to_bytes(32, "little"), dtype=np.uint8), (n, 1))
+            k_eq = 0x1234567890ABCDEF1234567890ABCDEF % R_ORDER
+            alt = const(7)
+            alt[1::2] = np.frombuffer(int(R_ORDER - 7).to_bytes(32, "little"), dtype=np.uint8)
+            sets = [("uniform", uni, None), ("rollup_like", roll, None), ("all_zero", const(0), 0),
+                    ("all_one", const(1), ssum % R_ORDER), ("all_rm1", const(R_ORDER - 1), (R_ORDER - 1) * ssum % R_ORDER),
+                    ("all_equal", const(k_eq), k_eq * ssum % R_ORDER), ("alternating_k_rmk", alt, None)]
+            mm = w_model(n) * (1 if group == 1 else 3)
+            for name, arr, e in sets:
+                if lg > 22 and name not in ("uniform", "rollup_like", "all_equal"):
+                    continue                                    # host-side scalar sets of 2^24+ x 32 B: keep the run short
+                k = np.ascontiguousarray(arr)
+                if e is None:
+                    e = dot_mod_r(k.reshape(-1), s64)
+                d_k = torch.from_numpy(k.reshape(-1)).cuda()
+                d_out = torch.zeros(256, dtype=torch.uint8, device="cuda")
+                best, med = timeit(lambda: _lib.check(L.zkr_msm_dev(ctx, bases, C.c_void_p(d_k.data_ptr()), n, C.c_void_p(d_out.data_ptr()))))
+                out = np.zeros(ab, dtype=np.uint8)
+                _lib.check(L.zkr_msm(ctx, bases, C.c_void_p(d_k.data_ptr()), n, 1, _lib.buf_ptr(out)))
+                ok = (out.tobytes() == host_g1_mul(e)) if group == 1 else host_g2_check(out.tobytes(), e)
+                row = dict(group=group, log_n=lg, scalars=name, c=cc.value, windows=ww.value, ms_best=round(best, 4),
+                           ms_median=round(med, 4), gpts_per_s=round(n / best / 1e6, 4), modmul_model=mm,
+                           frac_of_modmul_peak=round(mm / (best * 1e-3) / modmul_peak.value, 4),
+                           imad_frac_plain=round(mm * MODMUL_IMAD / (best * 1e-3) / imad_peak.value, 4),
+                           table_gb=round(nbytes.value / 1e9, 3), load_s=round(t_load, 2), correct=bool(ok))
+                if name == "uniform":
+                    cpu = {}
+                    if lg <= 22:
+                        box = {}
+                        tb = wall(lambda: box.update(r=cbind.msm(group, pts, k.reshape(-1), mode=1, threads=cores)))
+                        same = box["r"] == out.tobytes()
+                        cpu["cpu_b"] = dict(kind="port", algo="Pippenger, C restatement", cores=cores, seconds=round(tb, 3),
+                                            gpts_per_s=round(n / tb / 1e9, 6), gpu_speedup=round(tb * 1e3 / best, 1), result_equal=same)
+                    if lg <= 16:
+                        ta = wall(lambda: box.update(r=cbind.msm(group, pts, k.reshape(-1), mode=0, threads=1)))
+                        cpu["cpu_a"] = dict(kind="port", algo="snarkjs structure: one double-and-add per point", cores=1,
+                                            seconds=round(ta, 3), gpts_per_s=round(n / ta / 1e9, 6), gpu_speedup=round(ta * 1e3 / best, 1),
+                                            result_equal=box["r"] == out.tobytes())
+                    row["cpu_baseline"] = cpu
+                res["msm"].append(row)
+                print(json.dumps(row), flush=True)
+                del d_k
+            L.zkr_bases_free(bases)
+            del pts
+    cval, gval = 0x1234567890ABCDEF1234567890ABCDEF0F1E2D3C4B5A6978 % R_ORDER, 0x0FEDCBA9876543210FEDCBA987654321 % R_ORDER
+    cb = np.frombuffer(cval.to_bytes(32, "little"), dtype=np.uint8)
+    gb = np.frombuffer(gval.to_bytes(32, "little"), dtype=np.uint8)
+    import random
+    for lg in range(16, (args.sweep_max_log if "ntt" in args.sweep else 0) + 1, 2):
+        n = 1 << lg
+        w = pow(5, (R_ORDER - 1) >> lg, R_ORDER)
+        gsh = pow(5, (R_ORDER - 1) >> (lg + 1), R_ORDER)
+        d = torch.empty(n * 32, dtype=torch.uint8, device="cuda")
+        fill = lambda: _lib.check(L.zkr_fill_geometric(ctx, C.c_void_p(d.data_ptr()), n, _lib.buf_ptr(cb), _lib.buf_ptr(gb), 0, lg, 1, 0))
+        val = lambda k: int.from_bytes(d[32 * k:32 * k + 32].cpu().numpy().tobytes(), "little")
+        prng = random.Random(lg)
+        probes = [0, n - 1] + [prng.randrange(n) for _ in range(8)]
+        brev = lambda x: int(bin(x)[2:].zfill(lg)[::-1], 2)
+        ok = True
+        # forward (natural in, bit-reversed out): X[k] = c (g^N - 1) / (g w^k - 1)
+        fill()
+        _lib.check(L.zkr_ntt(ctx, C.c_void_p(d.data_ptr()), lg, 0 | 0x10, 1))
+        top = cval * (pow(gval, n, R_ORDER) - 1) % R_ORDER
+        for p_ in probes:
+            ok = ok and val(p_) == top * pow((gval * pow(w, brev(p_), R_ORDER) - 1) % R_ORDER, -1, R_ORDER) % R_ORDER
+        # coset forward: X[k] = x(gsh w^k) = c ((g gsh)^N - 1) / (g gsh w^k - 1)
+        fill()
+        _lib.check(L.zkr_ntt(ctx, C.c_void_p(d.data_ptr()), lg, 2 | 0x10, 1))
+        g2 = gval * gsh % R_ORDER
+        top2 = cval * (pow(g2, n, R_ORDER) - 1) % R_ORDER
+        for p_ in probes[:5]:
+            ok = ok and val(p_) == top2 * pow((g2 * pow(w, brev(p_), R_ORDER) - 1) % R_ORDER, -1, R_ORDER) % R_ORDER
+        # round trip: DIT^-1(DIF(x)) == x
+        fill()
+        _lib.check(L.zkr_ntt(ctx, C.c_void_p(d.data_ptr()), lg, 0 | 0x10, 1))
+        _lib.check(L.zkr_ntt(ctx, C.c_void_p(d.data_ptr()), lg, 1 | 0x20, 1))
+        ref = torch.empty_like(d)
+        _lib.check(L.zkr_fill_geometric(ctx, C.c_void_p(ref.data_ptr()), n, _lib.buf_ptr(cb), _lib.buf_ptr(gb), 0, lg, 1, 0))
+        torch.cuda.synchronize()
+        ok = ok and bool(torch.equal(ref, d))
+        del ref
+        cpu = {}
+        if lg <= 22:
+            x = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+            x[:, 31] &= 0x1F
+            xb = np.ascontiguousarray(x).reshape(-1)
+            tb = wall(lambda: cbind.ntt(xb.copy(), lg, False, False, 1, cores))
+            cpu["cpu_b"] = dict(kind="port", algo="iterative radix-2, C restatement", cores=cores, seconds=round(tb, 4),
+                                gb_per_s=round(64.0 * n / tb / 1e9, 3))
+            if lg <= 20:
+                ta = wall(lambda: cbind.ntt(xb.copy(), lg, False, False, 0, 1))
+                cpu["cpu_a"] = dict(kind="port", algo="snarkjs polfield structure: recursive radix-2", cores=1, seconds=round(ta, 4),
+                                    gb_per_s=round(64.0 * n / ta / 1e9, 3))
+        for name, mode in (("forward_dif", 0 | 0x10), ("inverse_dit", 1 | 0x20), ("coset_forward_dif", 2 | 0x10)):
+            best, med = timeit(lambda: _lib.check(L.zkr_ntt(ctx, C.c_void_p(d.data_ptr()), lg, mode, 1)))
+            mm = (n // 2) * lg
+            row = dict(log_n=lg, op=name, ms_best=round(best, 4), ms_median=round(med, 4), gb_per_s=round(64.0 * n / (best * 1e-3) / 1e9, 1),
+                       butterfly_modmul_frac_of_peak=round(mm / (best * 1e-3) / modmul_peak.value, 4),
+                       imad_frac_plain=round(mm * MODMUL_IMAD / (best * 1e-3) / imad_peak.value, 4), correct=bool(ok))
+            if name == "forward_dif":
+                row["cpu_baseline"] = cpu
+                for kk in cpu.values():
+                    kk["gpu_speedup"] = round(kk["seconds"] * 1e3 / best, 1)
+            res["ntt"].append(row)
+            print(json.dumps(row), flush=True)
+        del d
+    gp.close()
+    if args.sweep_out:
+        os.makedirs(os.path.dirname(args.sweep_out) or ".", exist_ok=True)
+        json.dump(res, open(args.sweep_out, "w"), indent=1)
+
+
 def _lib_check(rc):
     from simple_zk_rollups_b200 import _lib
     _lib.check(rc)
@@ -836,9 +1028,15 @@ def main():
     ap.add_argument("--sharded-ntt-logs", default="24,26")
     ap.add_argument("--sharded-msm-log", type=int, default=24)
     ap.add_argument("--make-key", default=None, help=argparse.SUPPRESS)
+    ap.add_argument("--sweep", default="", help="msm,ntt: BASELINE configs[2..3] sweeps on one GPU with CPU baselines beside every row")
+    ap.add_argument("--sweep-max-log", type=int, default=26)
+    ap.add_argument("--sweep-out", default=None)
     args = ap.parse_args()
     if args.make_key:
         make_key(args)
+        return
+    if args.sweep:
+        run_sweep(args)
         return
     if args.warmup < 3 and args.impl == "ours":
         log("[bench] note: timing rules ask for >= 3 warm-up steps")

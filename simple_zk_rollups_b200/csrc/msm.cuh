@@ -566,9 +566,11 @@ struct MsmWork {                      // per-bases device work buffers
 //                 caller has made `st` wait for that set's ev_sorted.
 //   ev_sorted   : recorded on st once the sorted pairs are final.
 //   ev_accum    : recorded on st after the level-1 accumulation (the bulk of the MSM) has been queued.
+//   wait_accum  : st waits for this event right before the level-1 accumulation is queued (digit extraction and the
+//                 sort, small kernels, may run ahead of it).
 struct MsmHooks {
     const zkr_bases* sorted_from = nullptr;
-    cudaEvent_t ev_sorted = nullptr, ev_accum = nullptr;
+    cudaEvent_t ev_sorted = nullptr, ev_accum = nullptr, wait_accum = nullptr;
 };
 
 }  // namespace zkr
@@ -748,6 +750,7 @@ int msm_run(zkr_ctx* ctx, cudaStream_t st, const zkr_bases* b, const uint32_t* d
     const size_t smem = (size_t)(kAccumThreads / 32) * 2 * 32 * (L + 1) * 4;
     XYZZ<F>* buckets = (XYZZ<F>*)wk.buckets;
     const int pslot = ctx->prof_begin(sizeof(F) == 32 ? PROF_ACCUM_G1 : PROF_ACCUM_G2, st, (double)total);
+    if (hooks && hooks->wait_accum) ZKR_CUDA(cudaStreamWaitEvent(st, hooks->wait_accum, 0));
     // ZKR_MSM_LEVELS=1: the round-1 recursive boundary levels instead of the one-launch gather (A/B knob)
     static const bool use_levels = getenv("ZKR_MSM_LEVELS") && atoi(getenv("ZKR_MSM_LEVELS")) != 0;
     if (!use_levels) {

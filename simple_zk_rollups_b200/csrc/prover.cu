@@ -498,37 +498,39 @@ static int prove_enqueue(zkr_ctx* ctx, const zkr_pkey* pk, char* d_proof, bool t
     }
     // heaviest first: the G2 MSM costs ~3 G1 MSMs
     // ZKR_DELAY (experiment knob): chains named in it (A, B = B1', C, H = the hExps MSM) start their MSM only once the
-    // G2 accumulation kernel is done, so that their bulk overlaps the G2 chain's latency-bound tail
+    // G2 accumulation kernel is done, so that their bulk overlaps the G2 chain's latency-bound tail.  Lower case
+    // (a, b, c, h): only the chain's level-1 accumulation waits; its digit extraction and sort run ahead.
     static const char* delay = getenv("ZKR_DELAY") ? getenv("ZKR_DELAY") : "";
     auto delayed = [&](char who, cudaStream_t s) -> int {
         if (par && strchr(delay, who)) ZKR_CUDA(cudaStreamWaitEvent(s, pk->ev_b2_accum, 0));
         return ZKR_OK;
     };
+    auto late = [&](char who) -> cudaEvent_t { return (par && strchr(delay, who)) ? pk->ev_b2_accum : nullptr; };
     if (timed) cudaEventRecord(ev[6], sB2);
     ZKR_TRY(msm_run_g2(ctx, sB2, pk->B2, w, pk->res + R_B2, nullptr, pk->ev_b2_sorted, pk->ev_b2_accum));
     if (timed) cudaEventRecord(ev[7], sB2);
     // H chain
     if (!(h_first && par)) ZKR_TRY(h_front());
     ZKR_TRY(delayed('H', sH));
-    ZKR_TRY(msm_run_g1(ctx, sH, pk->H, (const uint32_t*)(pk->h + pk->h_lo), pk->res + R_H));
+    ZKR_TRY(msm_run_g1(ctx, sH, pk->H, (const uint32_t*)(pk->h + pk->h_lo), pk->res + R_H, nullptr, nullptr, nullptr, late('h')));
     if (timed) cudaEventRecord(ev[3], sH);
     // A, then s * pi_a
     if (timed) cudaEventRecord(ev[4], sA);
     ZKR_TRY(delayed('A', sA));
-    ZKR_TRY(msm_run_g1(ctx, sA, pk->A, w, pk->res + R_A));
+    ZKR_TRY(msm_run_g1(ctx, sA, pk->A, w, pk->res + R_A, nullptr, nullptr, nullptr, late('a')));
     if (timed) cudaEventRecord(ev[5], sA);
     if (timed) cudaEventRecord(ev[8], sB1);
     ZKR_TRY(delayed('B', sB1));
     if (pk->share_b_sort) {
         ZKR_CUDA(cudaStreamWaitEvent(sB1, pk->ev_b2_sorted, 0));
-        ZKR_TRY(msm_run_g1(ctx, sB1, pk->B1, w, pk->res + R_B1, pk->B2));
+        ZKR_TRY(msm_run_g1(ctx, sB1, pk->B1, w, pk->res + R_B1, pk->B2, nullptr, nullptr, late('b')));
     } else {
-        ZKR_TRY(msm_run_g1(ctx, sB1, pk->B1, w, pk->res + R_B1));
+        ZKR_TRY(msm_run_g1(ctx, sB1, pk->B1, w, pk->res + R_B1, nullptr, nullptr, nullptr, late('b')));
     }
     if (timed) cudaEventRecord(ev[9], sB1);
     if (timed) cudaEventRecord(ev[10], sC);
     ZKR_TRY(delayed('C', sC));
-    ZKR_TRY(msm_run_g1(ctx, sC, pk->C, w, pk->res + R_C));
+    ZKR_TRY(msm_run_g1(ctx, sC, pk->C, w, pk->res + R_C, nullptr, nullptr, nullptr, late('c')));
     if (timed) cudaEventRecord(ev[11], sC);
     if (comm && comm->world > 1) {
         // sharded: the five results are partial sums over this rank's point ranges.  Store them into every
