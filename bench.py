@@ -510,7 +510,7 @@ def sharded_blocks(env, args, key_rank0):
     ctx = gp.ctx
     reps = 5
     ntt_logs = [int(v) for v in args.sharded_ntt_logs.split(",") if v]
-    msm_log = args.sharded_msm_log
+    msm_logs = [int(v) for v in str(args.sharded_msm_log).split(",") if v]
     comm = sh.Comm(ctx, rank, world, (1 << max(ntt_logs + [16])) // world)
     comm.connect_torch()
     res = {"n_gpus": world, "transport": "peer memory over NVLink (CUDA IPC mapped slabs, remote stores from the producing kernels, "
@@ -638,80 +638,83 @@ def sharded_blocks(env, args, key_rank0):
         log("[bench] sharded NTT 2^%d: dif %.3f ms (1 GPU %.3f), identical=%s (%.1f s)" % (lg, t_dif, t_single, row["identical"], time.time() - t0))
 
     # ------------------------------------------------------------------ G1 MSM sharded by point range
-    t0 = time.time()
-    n = 1 << msm_log
-    chunks = 8                                        # generator granularity: the same vectors for every world size
-    cn = n // chunks
+    res["msm_g1"] = []
+    for msm_log in msm_logs:
+        t0 = time.time()
+        n = 1 << msm_log
+        chunks = 8                                        # generator granularity: the same vectors for every world size
+        cn = n // chunks
 
-    def chunk(j):
-        g_ = np.random.default_rng(5000 + 16 * msm_log + j)
-        s64 = g_.integers(1, 1 << 63, size=cn, dtype=np.uint64)
-        k = g_.integers(0, 256, size=(cn, 32), dtype=np.uint8)
-        k[:, 31] &= 0x1F                              # < 2^253 < r
-        sel = g_.random(cn) < 0.03                    # rollup-like: 3 % of the scalars in {0, 1}
-        k[sel] = 0
-        k[sel, 0] = g_.integers(0, 2, size=int(sel.sum()), dtype=np.uint8)
-        return s64, k
+        def chunk(j):
+            g_ = np.random.default_rng(5000 + 16 * msm_log + j)
+            s64 = g_.integers(1, 1 << 63, size=cn, dtype=np.uint64)
+            k = g_.integers(0, 256, size=(cn, 32), dtype=np.uint8)
+            k[:, 31] &= 0x1F                              # < 2^253 < r
+            sel = g_.random(cn) < 0.03                    # rollup-like: 3 % of the scalars in {0, 1}
+            k[sel] = 0
+            k[sel, 0] = g_.integers(0, 2, size=int(sel.sum()), dtype=np.uint8)
+            return s64, k
 
-    def make_bases(lo, hi):
-        js = range(lo // cn, hi // cn)
-        parts = [chunk(j) for j in js]
-        s64 = np.concatenate([p_[0] for p_ in parts])
-        k = np.concatenate([p_[1] for p_ in parts])
-        sc = np.zeros((hi - lo, 32), dtype=np.uint8)
-        sc[:, :8] = s64.view(np.uint8).reshape(hi - lo, 8)
-        pts = np.empty((hi - lo) * 64, dtype=np.uint8)
-        _lib_check(L.zkr_synth_points(ctx, 1, _buf_ptr(sc), hi - lo, _buf_ptr(pts)))
-        bases = C.c_void_p()
-        _lib_check(L.zkr_bases_load(ctx, 1, _buf_ptr(pts), hi - lo, 0, C.byref(bases)))
-        d_k = torch.from_numpy(np.ascontiguousarray(k).reshape(-1)).cuda()
-        return bases, d_k, s64, k
+        def make_bases(lo, hi):
+            js = range(lo // cn, hi // cn)
+            parts = [chunk(j) for j in js]
+            s64 = np.concatenate([p_[0] for p_ in parts])
+            k = np.concatenate([p_[1] for p_ in parts])
+            sc = np.zeros((hi - lo, 32), dtype=np.uint8)
+            sc[:, :8] = s64.view(np.uint8).reshape(hi - lo, 8)
+            pts = np.empty((hi - lo) * 64, dtype=np.uint8)
+            _lib_check(L.zkr_synth_points(ctx, 1, _buf_ptr(sc), hi - lo, _buf_ptr(pts)))
+            bases = C.c_void_p()
+            _lib_check(L.zkr_bases_load(ctx, 1, _buf_ptr(pts), hi - lo, 0, C.byref(bases)))
+            d_k = torch.from_numpy(np.ascontiguousarray(k).reshape(-1)).cuda()
+            return bases, d_k, s64, k
 
-    lo, hi = rank * (n // world), (rank + 1) * (n // world)
-    bases, d_k, s64, k = make_bases(lo, hi)
-    e_part = dot_mod_r(k.reshape(-1), s64)            # this rank's share of sum k_i s_i, on the host
-    outp = comm.msm(bases, d_k.data_ptr(), hi - lo, on_device=True)[:64].tobytes()
-    t_msm = best_of(env, lambda: comm.msm(bases, d_k.data_ptr(), hi - lo, on_device=True), reps)
-    cc, ww = C.c_int(), C.c_int()
-    _lib_check(L.zkr_bases_info(bases, None, C.byref(cc), C.byref(ww), None))
-    L.zkr_bases_free(bases)
-    del d_k
-    parts = [None] * world
-    dist.all_gather_object(parts, (int(e_part), outp))
-    e = sum(p_[0] for p_ in parts) % R_ORDER
-    ok = all(p_[1] == parts[0][1] for p_ in parts) and outp == host_g1_mul(e)
-    # single-GPU baseline on rank 0 (the other ranks wait)
-    t_single = 0.0
-    if rank == 0:
-        b1, dk1, s1, k1 = make_bases(0, n)
-        o1 = np.zeros(64, dtype=np.uint8)
-        _lib_check(L.zkr_msm(ctx, b1, C.c_void_p(dk1.data_ptr()), n, 1, _buf_ptr(o1)))
-        ok = ok and o1.tobytes() == outp
-        d_out = torch.zeros(256, dtype=torch.uint8, device="cuda")
-        fn = lambda: _lib_check(L.zkr_msm_dev(ctx, b1, C.c_void_p(dk1.data_ptr()), n, C.c_void_p(d_out.data_ptr())))
-        fn()
-        torch.cuda.synchronize()
-        for _ in range(reps):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
+        lo, hi = rank * (n // world), (rank + 1) * (n // world)
+        bases, d_k, s64, k = make_bases(lo, hi)
+        e_part = dot_mod_r(k.reshape(-1), s64)            # this rank's share of sum k_i s_i, on the host
+        outp = comm.msm(bases, d_k.data_ptr(), hi - lo, on_device=True)[:64].tobytes()
+        t_msm = best_of(env, lambda: comm.msm(bases, d_k.data_ptr(), hi - lo, on_device=True), reps)
+        cc, ww = C.c_int(), C.c_int()
+        _lib_check(L.zkr_bases_info(bases, None, C.byref(cc), C.byref(ww), None))
+        L.zkr_bases_free(bases)
+        del d_k
+        parts = [None] * world
+        dist.all_gather_object(parts, (int(e_part), outp))
+        e = sum(p_[0] for p_ in parts) % R_ORDER
+        ok = all(p_[1] == parts[0][1] for p_ in parts) and outp == host_g1_mul(e)
+        # single-GPU baseline on rank 0 (the other ranks wait)
+        t_single = 0.0
+        if rank == 0:
+            b1, dk1, s1, k1 = make_bases(0, n)
+            o1 = np.zeros(64, dtype=np.uint8)
+            _lib_check(L.zkr_msm(ctx, b1, C.c_void_p(dk1.data_ptr()), n, 1, _buf_ptr(o1)))
+            ok = ok and o1.tobytes() == outp
+            d_out = torch.zeros(256, dtype=torch.uint8, device="cuda")
+            fn = lambda: _lib_check(L.zkr_msm_dev(ctx, b1, C.c_void_p(dk1.data_ptr()), n, C.c_void_p(d_out.data_ptr())))
             fn()
-            e1.record(stream)
             torch.cuda.synchronize()
-            t_single = e0.elapsed_time(e1) if t_single == 0.0 else min(t_single, e0.elapsed_time(e1))
-        L.zkr_bases_free(b1)
-        del dk1
-    t_single = env["max_over_ranks"](t_single)
-    res["msm_g1"] = {"log_n": msm_log, "ms": round(t_msm, 4), "single_gpu_ms": round(t_single, 4),
-                     "speedup_vs_1gpu": round(t_single / t_msm, 3), "gpts_per_s": round(n / t_msm / 1e6, 4),
-                     "window_bits_per_rank": cc.value, "windows": ww.value, "exchange_bytes_per_rank": 128 * (world - 1),
-                     "identical": bool(env["all_true"](ok)),
-                     "check": "P_i = s_i G (64-bit s_i), rollup-like scalars: every rank's result == (sum k_i s_i mod r) G with the sum "
-                              "(numpy 16-bit-limb dot products) and the scalar multiplication (Python ints) on the host; == the 1-GPU MSM",
-                     "limited_by": "fixed per-MSM latency (radix-sort passes, boundary levels, bucket reduction) at 2^%d points per rank" % (msm_log - (world.bit_length() - 1))}
-    log("[bench] sharded MSM 2^%d: %.3f ms on %d GPUs vs %.3f ms on one, identical=%s (%.1f s)" % (
-        msm_log, t_msm, world, t_single, res["msm_g1"]["identical"], time.time() - t0))
+            for _ in range(reps):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                fn()
+                e1.record(stream)
+                torch.cuda.synchronize()
+                t_single = e0.elapsed_time(e1) if t_single == 0.0 else min(t_single, e0.elapsed_time(e1))
+            L.zkr_bases_free(b1)
+            del dk1
+        t_single = env["max_over_ranks"](t_single)
+        row = {"log_n": msm_log, "ms": round(t_msm, 4), "single_gpu_ms": round(t_single, 4),
+                         "speedup_vs_1gpu": round(t_single / t_msm, 3), "gpts_per_s": round(n / t_msm / 1e6, 4),
+                         "window_bits_per_rank": cc.value, "windows": ww.value, "exchange_bytes_per_rank": 128 * (world - 1),
+                         "identical": bool(env["all_true"](ok)),
+                         "check": "P_i = s_i G (64-bit s_i), rollup-like scalars: every rank's result == (sum k_i s_i mod r) G with the sum "
+                                  "(numpy 16-bit-limb dot products) and the scalar multiplication (Python ints) on the host; == the 1-GPU MSM",
+                         "limited_by": "fixed per-MSM latency (radix-sort passes, boundary levels, bucket reduction) at 2^%d points per rank" % (msm_log - (world.bit_length() - 1))}
+        res["msm_g1"].append(row)
+        log("[bench] sharded MSM 2^%d: %.3f ms on %d GPUs vs %.3f ms on one, identical=%s (%.1f s)" % (
+            msm_log, t_msm, world, t_single, row["identical"], time.time() - t0))
     comm.close()
-    res["identical"] = bool(res["proof"]["identical"] and all(r_["identical"] for r_ in res["ntt"]) and res["msm_g1"]["identical"])
+    res["identical"] = bool(res["proof"]["identical"] and all(r_["identical"] for r_ in res["ntt"] + res["msm_g1"]))
     return res
 
 
@@ -763,6 +766,8 @@ def run_sweep(args):
         return time.time() - t0
 
     def host_g2_check(out, e):                     # G2 expectation: one fixed-base multiplication on the GPU (other kernel)
+        if e % R_ORDER == 0:
+            return out == bytes(128)               # the point at infinity is encoded as zeros
         esc = np.frombuffer(int(e).to_bytes(32, "little"), dtype=np.uint8).copy()
         exp_m = np.empty(128, dtype=np.uint8)
         _lib.check(L.zkr_synth_points(ctx, 2, _lib.buf_ptr(esc), 1, _lib.buf_ptr(exp_m)))
@@ -1026,7 +1031,7 @@ def main():
     ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the sharded proof / NTT / MSM block")
     ap.add_argument("--no-batch-2p22", action="store_true", help="skip the BASELINE configs[4] batch block")
     ap.add_argument("--sharded-ntt-logs", default="24,26")
-    ap.add_argument("--sharded-msm-log", type=int, default=24)
+    ap.add_argument("--sharded-msm-log", default="24", help="comma list of log2 sizes of the sharded G1 MSM")
     ap.add_argument("--make-key", default=None, help=argparse.SUPPRESS)
     ap.add_argument("--sweep", default="", help="msm,ntt: BASELINE configs[2..3] sweeps on one GPU with CPU baselines beside every row")
     ap.add_argument("--sweep-max-log", type=int, default=26)

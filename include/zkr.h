@@ -153,6 +153,28 @@ int zkr_prove_batch(zkr_ctx* const* ctxs, const zkr_pkey* const* pks, int n_ctx,
                     const void* const* witnesses, size_t n_signals, int n_proofs,
                     const void* rs32 /* n_proofs x 64 B (r|s), or NULL = fresh CSPRNG pairs */, void* out_proofs);
 
+/* ---- witness generation for forward-solvable constraint systems ---------
+ * Stands where the reference calls circom's generated calculator, circuit.calculateWitness(inputs)
+ * (operator/src/snarks/common.ts:12-17), for circuits whose constraints each introduce at most one new
+ * signal -- the one with the largest index -- and only in C:  new = ((A.w)(B.w) - C'.w) / c_new.  MiMC /
+ * Feistel rounds (prover/circuits/hasher.circom:8), products and linear combinations are of this form;
+ * signals no constraint defines that way (circuit inputs, bits under b (b - 1) = 0, circom `<--` hints)
+ * are GIVEN by the caller.  zkr_wprog_build analyses the R1CS once per circuit (r1cs: the circuit's own
+ * constraints, WITHOUT the input-consistency rows a snarkjs setup adds to polsA; zkr_r1cs_csc is declared
+ * below); ZKR_E_UNSUPPORTED if a row uses a signal that only a later row defines.
+ * zkr_wprog_given lists the signals the caller must supply (ascending; signal 0, the constant 1, is one
+ * of them).  zkr_witness_solve takes their values (n_given x 32 B std form, HOST memory, that order) and
+ * leaves the complete witness in DEVICE memory (d_witness: n_vars x 32 B std form), ready for
+ * zkr_prove_dev: one kernel launch per level of the dependency graph, no host round trip.
+ * Errors: ZKR_E_WITNESS_RANGE if a given value is >= r. */
+typedef struct zkr_wprog zkr_wprog;
+struct zkr_r1cs_csc;
+int zkr_wprog_build(zkr_ctx* ctx, const struct zkr_r1cs_csc* r1cs, zkr_wprog** out);
+void zkr_wprog_free(zkr_wprog* wp);
+int zkr_wprog_info(const zkr_wprog* wp, uint32_t* n_vars, uint32_t* n_given, uint32_t* n_solved, uint32_t* n_levels);
+int zkr_wprog_given(const zkr_wprog* wp, uint32_t* out_signals /* n_given */);
+int zkr_witness_solve(zkr_ctx* ctx, const zkr_wprog* wp, const void* given_values, void* d_witness);
+
 /* ---- verify -------------------------------------------------- */
 /* Replaces snarkjs groth.isValid(verifyingKey, proof, publicSignals) at
  * operator/src/snarks/common.ts:30-34 with the on-chain predicate of
@@ -322,7 +344,10 @@ int zkr_test_curve_op(zkr_ctx* ctx, int group, int op, const void* p, const void
 int zkr_test_bases_peek(const zkr_bases* b, int what, size_t offset, void* out, size_t bytes);
 /* integer-pipe microbenchmarks: which: 0 = IMAD chain, 1 = IMAD.WIDE chain, 2 = Fq modmul chain,
  * 3 = XYZZ mixed-add chain, 4 = DFMA chain (FP64 pipe), 5 = DFMA + IMAD.WIDE pairs, 6 = DFMA + 64-bit
- * add pairs, 7 = 64-bit add chain.  Returns operations per second (IMADs / modmuls / madds / pairs). */
+ * add pairs, 7 = 64-bit add chain; 8 = Fermat inversions, 9 = binary-Euclid inversions (full grids), 10 / 11 =
+ * batched-affine additions with one inversion per thread and 16 / 64 additions (the measurement behind the
+ * "batched affine" entry of DESIGN.md 4.8).  Returns operations per second (IMADs / modmuls / madds / pairs /
+ * inversions / additions). */
 int zkr_microbench(zkr_ctx* ctx, int which, int iters, double* ops_per_s, float* ms);
 
 #ifdef __cplusplus

@@ -69,6 +69,11 @@ _SIGS = {
     "zkr_prove_check": (C.c_int, [C.c_void_p, C.c_void_p]),
     "zkr_fill_geometric": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int,
                                      C.c_int, C.c_int]),
+    "zkr_wprog_build": (C.c_int, [C.c_void_p, C.POINTER(R1csCsc), C.POINTER(C.c_void_p)]),
+    "zkr_wprog_free": (None, [C.c_void_p]),
+    "zkr_wprog_info": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_uint32)] * 4),
+    "zkr_wprog_given": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "zkr_witness_solve": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "zkr_prove_batch": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int,
                                   C.POINTER(C.c_void_p), C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]),
     "zkr_bases_load": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]),

@@ -82,9 +82,9 @@ extern "C" int zkr_ctx_create(int device, zkr_ctx** out) {
         // (profiles/r01_pipeline_check.json).  The GPU is saturated by the proof's bulk kernels; ordering them does
         // not change the total.  (A first sweep with r = s = 0 favoured "B2 highest": with zero scalars the two
         // blinding multiplications are free, which hides that they then end up on the critical path.)
-        // s[0] = H chain, s[1] = A, s[2] = B1, s[3] = B2, s[4] = C.  ZKR_STREAM_PRIO="p0,p1,..." overrides (0 =
+        // s[0] = H chain, s[1] = A, s[2] = B1, s[3] = B2, s[4] = C, s[5] = the hExps MSM when ZKR_H_SPLIT=1.  ZKR_STREAM_PRIO="p0,p1,..." overrides (0 =
         // default, negative = higher).
-        static const int kDefaultPrio[kNumStreams] = {0, 0, 0, 0, 0, 0};
+        static const int kDefaultPrio[kNumStreams] = {0, 0, 0, 0, 0, 0, 0};
         int prio = kDefaultPrio[i];
         if (const char* e = getenv("ZKR_STREAM_PRIO")) {
             const char* q = e;

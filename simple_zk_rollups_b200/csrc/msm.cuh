@@ -222,20 +222,64 @@ k_accum_affine(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ v
 //                          inside the chunk, in which case level 1 has already stored the complete bucket;
 //     threads t0+1 .. t1 = (hi-1) / L : their HEAD slots (the run starts their chunk).
 // One thread per bucket adds them (about run length / L + 1 additions: ~7 at 2^20); buckets with more than kHeavyRun
-// partials (the {0, 1} witness skew, adversarial scalar sets) go to a list that k_bucket_gather_heavy sums with one
-// CTA per bucket.
-constexpr int kGatherThreads = 64;
+// partials (the {0, 1} witness skew, adversarial scalar sets) are summed by whole CTAs of the same launch.
+constexpr int kGatherThreads = 128;
 constexpr uint32_t kHeavyRun = 48;
 constexpr uint32_t kNoRun = 0xffffffffu;
-constexpr int kHeavyThreads = 128;
-constexpr int kHeavyBlocks = 64;
+constexpr int kHeavyBlocks = 32;
 
+// Blocks [0, kHeavyBlocks) are the heavy path, launched first so that their few long chains run beside the light
+// blocks of the same launch: the heavy blocks scan the run bounds (chunks of buckets dealt round-robin) and sum each
+// bucket that has more than kHeavyRun partials with all their threads (strided partial sums, then a tree in shared memory).
+// Blocks [kHeavyBlocks, ...) are the light path: one thread per bucket.
 template <class F>
 __global__ void __launch_bounds__(kGatherThreads)
 k_bucket_gather(const uint32_t* __restrict__ keys, uint32_t total, int logL, const uint32_t* __restrict__ run_lo,
-                const uint32_t* __restrict__ run_hi, const XYZZ<F>* __restrict__ bnd, XYZZ<F>* __restrict__ buckets,
-                uint32_t nbuckets, uint32_t* __restrict__ heavy, uint32_t* __restrict__ n_heavy) {
-    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+                const XYZZ<F>* __restrict__ bnd, XYZZ<F>* __restrict__ buckets, uint32_t nbuckets) {
+    extern __shared__ unsigned char smraw[];
+    const uint32_t* run_hi = run_lo + nbuckets;
+    if (blockIdx.x < kHeavyBlocks) {
+        XYZZ<F>* sp = reinterpret_cast<XYZZ<F>*>(smraw);
+        __shared__ uint32_t found[kGatherThreads];
+        __shared__ uint32_t n_found;
+        for (uint32_t chunk = blockIdx.x; chunk * kGatherThreads < nbuckets; chunk += kHeavyBlocks) {
+            // chunks of kGatherThreads consecutive buckets, dealt round-robin to the heavy blocks (coalesced scan, and an
+            // adversarial cluster of heavy buckets still spreads over the blocks); most chunks hold none: one barrier
+            const uint32_t b = chunk * kGatherThreads + threadIdx.x;
+            bool is_heavy = false;
+            if (b < nbuckets) {
+                const uint32_t lo = run_lo[b];
+                is_heavy = lo != kNoRun && (((run_hi[b] - 1) >> logL) - (lo >> logL) + 1) > kHeavyRun;
+            }
+            if (__syncthreads_count(is_heavy) == 0) continue;
+            if (threadIdx.x == 0) n_found = 0;
+            __syncthreads();
+            if (is_heavy) found[atomicAdd(&n_found, 1u)] = b;
+            __syncthreads();
+            const uint32_t nf = n_found;
+            for (uint32_t f = 0; f < nf; f++) {
+                const uint32_t hb = found[f];
+                const uint32_t lo = run_lo[hb], hi = run_hi[hb];
+                const uint32_t t0 = lo >> logL, t1 = (hi - 1) >> logL;
+                const bool aligned = lo == (t0 << logL);
+                XYZZ<F> acc = XYZZ<F>::identity();
+#pragma unroll 1
+                for (uint32_t t = t0 + threadIdx.x; t <= t1; t += kGatherThreads)
+                    acc.add(XYZZ<F>::load(bnd + 2 * (size_t)t + ((t == t0 && !aligned) ? 1 : 0)));
+                sp[threadIdx.x] = acc;
+                __syncthreads();
+                for (int d = kGatherThreads / 2; d >= 1; d >>= 1) {
+                    if ((int)threadIdx.x < d) xyzz_add_mem(&sp[threadIdx.x], &sp[threadIdx.x], &sp[threadIdx.x + d]);
+                    __syncthreads();
+                }
+                if (threadIdx.x == 0) sp[0].store(buckets + hb);
+                __syncthreads();
+            }
+            __syncthreads();
+        }
+        return;
+    }
+    const uint32_t b = (blockIdx.x - kHeavyBlocks) * blockDim.x + threadIdx.x;
     if (b >= nbuckets) return;
     const uint32_t lo = run_lo[b];
     if (lo == kNoRun) return;                         // empty bucket: stays the identity (memset)
@@ -249,43 +293,11 @@ k_bucket_gather(const uint32_t* __restrict__ keys, uint32_t total, int logL, con
         else if (to_end) XYZZ<F>::load(bnd + 2 * (size_t)t0 + 1).store(buckets + b);
         return;
     }
-    if (t1 - t0 + 1 > kHeavyRun) {
-        heavy[atomicAdd(n_heavy, 1u)] = b;
-        return;
-    }
+    if (t1 - t0 + 1 > kHeavyRun) return;              // summed by a heavy block of this launch
     XYZZ<F> acc = XYZZ<F>::load(bnd + 2 * (size_t)t0 + (aligned ? 0 : 1));
 #pragma unroll 1
     for (uint32_t t = t0 + 1; t <= t1; t++) acc.add(XYZZ<F>::load(bnd + 2 * (size_t)t));
     acc.store(buckets + b);
-}
-
-// one CTA per heavy bucket (grid-stride over the list): strided partial sums per thread, then a tree in shared memory
-template <class F>
-__global__ void __launch_bounds__(kHeavyThreads)
-k_bucket_gather_heavy(int logL, const uint32_t* __restrict__ run_lo, const uint32_t* __restrict__ run_hi,
-                      const XYZZ<F>* __restrict__ bnd, XYZZ<F>* __restrict__ buckets, const uint32_t* __restrict__ heavy,
-                      const uint32_t* __restrict__ n_heavy) {
-    extern __shared__ unsigned char smraw[];
-    XYZZ<F>* sp = reinterpret_cast<XYZZ<F>*>(smraw);
-    const uint32_t n = *n_heavy;
-    for (uint32_t h = blockIdx.x; h < n; h += gridDim.x) {
-        const uint32_t b = heavy[h];
-        const uint32_t lo = run_lo[b], hi = run_hi[b];
-        const uint32_t t0 = lo >> logL, t1 = (hi - 1) >> logL;
-        const bool aligned = lo == (t0 << logL);
-        XYZZ<F> acc = XYZZ<F>::identity();
-#pragma unroll 1
-        for (uint32_t t = t0 + threadIdx.x; t <= t1; t += kHeavyThreads)
-            acc.add(XYZZ<F>::load(bnd + 2 * (size_t)t + ((t == t0 && !aligned) ? 1 : 0)));
-        sp[threadIdx.x] = acc;
-        __syncthreads();
-        for (int d = kHeavyThreads / 2; d >= 1; d >>= 1) {
-            if ((int)threadIdx.x < d) xyzz_add_mem(&sp[threadIdx.x], &sp[threadIdx.x], &sp[threadIdx.x + d]);
-            __syncthreads();
-        }
-        if (threadIdx.x == 0) sp[0].store(buckets + b);
-        __syncthreads();
-    }
 }
 
 // level >= 2: XYZZ partials (with sentinel holes) -> bucket sums / boundary partials
@@ -552,7 +564,6 @@ struct MsmWork {                      // per-bases device work buffers
     unsigned int* red_counter = nullptr;
     void* result = nullptr;           // 1 XYZZ
     uint32_t *run_lo = nullptr, *run_hi = nullptr;     // per bucket: [lo, hi) of its run in the sorted list (kNoRun = empty)
-    uint32_t *heavy = nullptr, *n_heavy = nullptr;     // buckets whose partials one CTA sums (k_bucket_gather_heavy)
     int* range_err = nullptr;
     size_t bytes = 0;
     // where the last radix sort left the sorted (bucket, point-ref) pairs: read by a second base set that shares them
@@ -691,9 +702,7 @@ int bases_build(zkr_ctx* ctx, zkr_bases* b, const char* h_points, size_t n_src, 
     ZKR_CUDA(cudaMalloc(&wk.result, XB));
     ZKR_CUDA(cudaMalloc(&wk.run_lo, 8 * (size_t)b->plan.nbuckets));
     wk.run_hi = wk.run_lo + b->plan.nbuckets;
-    ZKR_CUDA(cudaMalloc(&wk.heavy, 4 * (size_t)b->plan.nbuckets));
-    ZKR_CUDA(cudaMalloc(&wk.n_heavy, 4));
-    wk.bytes += 12 * (size_t)b->plan.nbuckets + 4;
+    wk.bytes += 8 * (size_t)b->plan.nbuckets;
     ZKR_CUDA(cudaMalloc(&wk.range_err, sizeof(int)));
     ZKR_CUDA(cudaMemsetAsync(wk.range_err, 0, sizeof(int), st));
     wk.bytes += wk.cub_bytes + XB * ((size_t)b->plan.nbuckets + bnd0 + bnd1 + nred + 1) + 4 * (bnd0 + bnd1);
@@ -704,7 +713,7 @@ int bases_build(zkr_ctx* ctx, zkr_bases* b, const char* h_points, size_t n_src, 
     ZKR_CUDA(cudaFuncSetAttribute(k_bucket_weighted<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(XB * kReduceThreads)));
     ZKR_CUDA(cudaFuncSetAttribute((k_accum_affine<F, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
     ZKR_CUDA(cudaFuncSetAttribute((k_accum_affine<F, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
-    ZKR_CUDA(cudaFuncSetAttribute(k_bucket_gather_heavy<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(XB * kHeavyThreads)));
+    ZKR_CUDA(cudaFuncSetAttribute(k_bucket_gather<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(XB * kGatherThreads)));
     ZKR_CUDA(cudaStreamSynchronize(st));
     return ZKR_OK;
 }
@@ -751,22 +760,20 @@ int msm_run(zkr_ctx* ctx, cudaStream_t st, const zkr_bases* b, const uint32_t* d
     XYZZ<F>* buckets = (XYZZ<F>*)wk.buckets;
     const int pslot = ctx->prof_begin(sizeof(F) == 32 ? PROF_ACCUM_G1 : PROF_ACCUM_G2, st, (double)total);
     if (hooks && hooks->wait_accum) ZKR_CUDA(cudaStreamWaitEvent(st, hooks->wait_accum, 0));
-    // ZKR_MSM_LEVELS=1: the round-1 recursive boundary levels instead of the one-launch gather (A/B knob)
-    static const bool use_levels = getenv("ZKR_MSM_LEVELS") && atoi(getenv("ZKR_MSM_LEVELS")) != 0;
-    if (!use_levels) {
-        ZKR_CUDA(cudaMemsetAsync(wk.run_lo, 0xff, 4 * (size_t)nb, st));
-        ZKR_CUDA(cudaMemsetAsync(wk.n_heavy, 0, 4, st));
-    }
+    // Boundary partials -> buckets: the one-launch gather up to 20-bit windows (every proof size), the round-1 recursive
+    // levels above (2M+ buckets of ~3 partials each: measured 48.1 vs 40.6 ms at 2^24, profiles/r02_msm_gather_vs_levels.json).
+    // ZKR_MSM_LEVELS = 0 / 1 forces the gather / the levels (A/B knob).
+    static const int force_levels = getenv("ZKR_MSM_LEVELS") ? atoi(getenv("ZKR_MSM_LEVELS")) : -1;
+    const bool use_levels = force_levels >= 0 ? force_levels != 0 : c > 20;
+    if (!use_levels) ZKR_CUDA(cudaMemsetAsync(wk.run_lo, 0xff, 4 * (size_t)nb, st));
     ZKR_LAUNCH(ctx, (k_accum_affine<F, kPrefetch>), b->T1p / kAccumThreads, kAccumThreads, smem, st, skeys, svals, total,
                b->logL, b->table, buckets, (XYZZ<F>*)wk.bnd[0], use_levels ? wk.bnd_keys[0] : nullptr, nb,
                use_levels ? nullptr : wk.run_lo);
     ctx->prof_end(sizeof(F) == 32 ? PROF_ACCUM_G1 : PROF_ACCUM_G2, pslot, st);
     if (hooks && hooks->ev_accum) ZKR_CUDA(cudaEventRecord(hooks->ev_accum, st));
     if (!use_levels) {
-        ZKR_LAUNCH(ctx, k_bucket_gather<F>, ceil_div(nb, kGatherThreads), kGatherThreads, 0, st, skeys, total, b->logL,
-                   wk.run_lo, wk.run_hi, (const XYZZ<F>*)wk.bnd[0], buckets, nb, wk.heavy, wk.n_heavy);
-        ZKR_LAUNCH(ctx, k_bucket_gather_heavy<F>, kHeavyBlocks, kHeavyThreads, XB * kHeavyThreads, st, b->logL, wk.run_lo,
-                   wk.run_hi, (const XYZZ<F>*)wk.bnd[0], buckets, wk.heavy, wk.n_heavy);
+        ZKR_LAUNCH(ctx, k_bucket_gather<F>, kHeavyBlocks + ceil_div(nb, kGatherThreads), kGatherThreads, XB * kGatherThreads,
+                   st, skeys, total, b->logL, wk.run_lo, (const XYZZ<F>*)wk.bnd[0], buckets, nb);
     }
     // boundary levels (round-1 path)
     size_t cnt = 2 * (size_t)b->T1p;

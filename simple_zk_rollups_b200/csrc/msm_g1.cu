@@ -80,7 +80,7 @@ void bases_release(zkr_bases* b) {
     MsmWork& w = b->work;
     void* ps[] = {b->src_index, b->table, w.keys[0], w.keys[1], w.vals[0], w.vals[1], w.cub_tmp, w.buckets,
                   w.bnd[0], w.bnd[1], w.bnd_keys[0], w.bnd_keys[1], w.red, w.red_counter, w.result, w.range_err,
-                  w.run_lo, w.heavy, w.n_heavy};
+                  w.run_lo};
     for (void* p : ps) cudaFree(p);
     delete b;
 }

@@ -142,8 +142,12 @@ struct PassFuse {
     int ld_op, st_op;
 };
 
-template <bool DIT, int MODE>
-__global__ void __launch_bounds__(256, 2)
+// RL = log2 of the register-stage radix.  RL = 3 (the only instantiation): a thread holds 8 elements = 3 butterfly levels
+// between two barriers, 112-128 registers, 2 CTAs / SM (4 warps per scheduler).  RL = 2 (two groups of 4 elements,
+// 2 levels per barrier, 80 registers, 3 CTAs / SM) was built and timed in round 2: 1-12 % SLOWER at every size
+// (profiles/r02_ntt_radix_ab.json) -- the extra shared-memory round trip per pass costs more than the extra warps hide.
+template <bool DIT, int MODE, int RL>
+__global__ void __launch_bounds__(256, RL == 3 ? 2 : 3)
 k_ntt_pass(Fr* __restrict__ data, int k, int c, int s, int ls_, int chunk_log, unsigned ctw_, const Fr* __restrict__ W,
            int kw, const Fr* __restrict__ tlo, const Fr* __restrict__ thi, int lb, int tw_shift, NttXchg xp, PassFuse fz) {
     extern __shared__ uint32_t sm[];
@@ -229,77 +233,94 @@ k_ntt_pass(Fr* __restrict__ data, int k, int c, int s, int ls_, int chunk_log, u
     }
     __syncthreads();
 
+    constexpr int G = 1 << RL;                // elements per register group
     int bit = DIT ? c : T - 1;
     while (DIT ? (bit <= T - 1) : (bit >= c)) {
         int lo, act_lo, act_hi;
         if (DIT) {
-            lo = bit > T - 3 ? T - 3 : bit;
+            lo = bit > T - RL ? T - RL : bit;
             act_lo = bit;
-            act_hi = lo + 2;
+            act_hi = lo + RL - 1;
         } else {
-            lo = bit < 2 ? 0 : bit - 2;
+            lo = bit < RL - 1 ? 0 : bit - (RL - 1);
             act_hi = bit;
             act_lo = lo > c ? lo : c;
         }
-        const int base = ((tid >> lo) << (lo + 3)) | (tid & ((1 << lo) - 1));
-        Fr x[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const uint32_t* p = sm + slot_of(base + (j << lo));
-#pragma unroll
-            for (int l = 0; l < 8; l++) x[j].v[l] = p[l * plane];
-        }
         const bool tw_now = !DIT && (s > 0) && (act_lo == c);     // DIF: after the last butterfly level (DIT: at load)
+#pragma unroll 1
+        for (int grp = 0; grp < (8 >> RL); grp++) {
+            const int gid = tid + grp * (tile >> 3);
+            const int base = ((gid >> lo) << (lo + RL)) | (gid & ((1 << lo) - 1));
+            Fr x[G];
 #pragma unroll
-        for (int ii = 0; ii < 3; ii++) {
-            const int i = DIT ? ii : 2 - ii;
-            const int p = lo + i;
-            if (p < act_lo || p > act_hi) continue;
-            const int pc = p - c;                  // butterfly half-size = 2^pc rows
+            for (int j = 0; j < G; j++) {
+                const uint32_t* p = sm + slot_of(base + (j << lo));
 #pragma unroll
-            for (int jl = 0; jl < (1 << i); jl++) {
-                Fr w;
-                if (pc > 0) {
-                    unsigned rowbits = ((unsigned)(base | (jl << lo)) >> c) & ((1u << pc) - 1);
-                    w = Fr::load_ro(W + ((size_t)rowbits << (kw - 1 - pc)));
-                }
+                for (int l = 0; l < 8; l++) x[j].v[l] = p[l * plane];
+            }
 #pragma unroll
-                for (int ju = 0; ju < (1 << (2 - i)); ju++) {
-                    const int j0 = jl | (ju << (i + 1));
-                    const int j1 = j0 | (1 << i);
-                    if (DIT) {
-                        if (pc > 0) x[j1] = x[j1] * w;
-                        const Fr u = x[j0], v = x[j1];
-                        x[j0] = u + v;
-                        x[j1] = u - v;
-                    } else {
-                        Fr u = x[j0], v = x[j1];
-                        x[j0] = u + v;
-                        Fr d = u - v;
-                        x[j1] = pc > 0 ? d * w : d;
+            for (int ii = 0; ii < RL; ii++) {
+                const int i = DIT ? ii : RL - 1 - ii;
+                const int p = lo + i;
+                if (p < act_lo || p > act_hi) continue;
+                const int pc = p - c;                  // butterfly half-size = 2^pc rows
+#pragma unroll
+                for (int jl = 0; jl < (1 << i); jl++) {
+                    Fr w;
+                    if (pc > 0) {
+                        unsigned rowbits = ((unsigned)(base | (jl << lo)) >> c) & ((1u << pc) - 1);
+                        w = Fr::load_ro(W + ((size_t)rowbits << (kw - 1 - pc)));
+                    }
+#pragma unroll
+                    for (int ju = 0; ju < (1 << (RL - 1 - i)); ju++) {
+                        const int j0 = jl | (ju << (i + 1));
+                        const int j1 = j0 | (1 << i);
+                        if (DIT) {
+                            if (pc > 0) x[j1] = x[j1] * w;
+                            const Fr u = x[j0], v = x[j1];
+                            x[j0] = u + v;
+                            x[j1] = u - v;
+                        } else {
+                            Fr u = x[j0], v = x[j1];
+                            x[j0] = u + v;
+                            Fr d = u - v;
+                            x[j1] = pc > 0 ? d * w : d;
+                        }
                     }
                 }
             }
-        }
-        if (!DIT && tw_now) {
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                int e = base + (j << lo);
-                unsigned rho = e >> c, col = e & cmask;
+            if (!DIT && tw_now) {
                 if (fz.twfull) {
-                    x[j] = x[j] * Fr::load_ro(fz.twfull + ((size_t)rho << s) + c0 + col);
+                    // software-pipelined: the table entry of element j + 1 is in flight while element j is multiplied
+                    // (r02 ncu: 14 % of the pass's stall samples were long_sb on the first IMAD.WIDE behind each load)
+                    auto tw_at = [&](int j) {
+                        const int e = base + (j << lo);
+                        return Fr::load_ro(fz.twfull + ((size_t)(e >> c) << s) + c0 + (e & cmask));
+                    };
+                    Fr tnext = tw_at(0);
+#pragma unroll
+                    for (int j = 0; j < G; j++) {
+                        const Fr t = tnext;
+                        if (j + 1 < G) tnext = tw_at(j + 1);
+                        x[j] = x[j] * t;
+                    }
                 } else {
-                    unsigned rev = __brev(rho) >> (32 - k);
-                    unsigned X = ((c0 + col) * rev) << tw_shift;
-                    x[j] = x[j] * (Fr::load_ro(tlo + (X & lbmask)) * Fr::load_ro(thi + (X >> lb)));
+#pragma unroll
+                    for (int j = 0; j < G; j++) {
+                        int e = base + (j << lo);
+                        unsigned rho = e >> c, col = e & cmask;
+                        unsigned rev = __brev(rho) >> (32 - k);
+                        unsigned X = ((c0 + col) * rev) << tw_shift;
+                        x[j] = x[j] * (Fr::load_ro(tlo + (X & lbmask)) * Fr::load_ro(thi + (X >> lb)));
+                    }
                 }
             }
-        }
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            uint32_t* p = sm + slot_of(base + (j << lo));
+            for (int j = 0; j < G; j++) {
+                uint32_t* p = sm + slot_of(base + (j << lo));
 #pragma unroll
-            for (int l = 0; l < 8; l++) p[l * plane] = x[j].v[l];
+                for (int l = 0; l < 8; l++) p[l * plane] = x[j].v[l];
+            }
         }
         __syncthreads();
         bit = DIT ? act_hi + 1 : act_lo - 1;
@@ -475,11 +496,15 @@ int ntt_get_tables(zkr_ctx* ctx, int log_n, NttTables** out) {
     // A process-wide "done" flag left the > 48 KB opt-in missing on every device but the first one a process used
     // (one process driving several GPUs: zkr_prove_batch / ProofQueue).
     {
-        ZKR_CUDA(cudaFuncSetAttribute((k_ntt_pass<false, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        ZKR_CUDA(cudaFuncSetAttribute((k_ntt_pass<true, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        ZKR_CUDA(cudaFuncSetAttribute((k_ntt_pass<false, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        ZKR_CUDA(cudaFuncSetAttribute((k_ntt_pass<true, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        ZKR_CUDA(cudaFuncSetAttribute((k_ntt_pass<true, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+#define ZKR_NTT_ATTR(...)                                                                                              \
+    ZKR_CUDA(cudaFuncSetAttribute((k_ntt_pass<__VA_ARGS__>), cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); \
+    ZKR_CUDA(cudaFuncSetAttribute((k_ntt_pass<__VA_ARGS__>), cudaFuncAttributePreferredSharedMemoryCarveout, 100))
+        ZKR_NTT_ATTR(false, 0, 3);
+        ZKR_NTT_ATTR(true, 0, 3);
+        ZKR_NTT_ATTR(false, 1, 3);
+        ZKR_NTT_ATTR(true, 2, 3);
+        ZKR_NTT_ATTR(true, 3, 3);
+#undef ZKR_NTT_ATTR
     }
     NttTables* t = new NttTables();
     t->log_n = log_n;
@@ -529,10 +554,13 @@ static int launch_pass(zkr_ctx* ctx, cudaStream_t st, const NttTables* t, Fr* da
     // the pass whose write-back is the all-to-all (remote stores) is timed on its own: bench.py's exchange GB/s
     const int pid = (MODE == 1 || MODE == 2) ? PROF_NTT_XCHG : PROF_NTT_PASS;
     const int pslot = ctx->prof_begin(pid, st, prof_units);
-    if (dit) ZKR_LAUNCH(ctx, (k_ntt_pass<true, MODE == 1 ? 3 : MODE>), g.blocks, threads, smem, st, data, g.k, g.c, g.s,
-                        g.ls, g.chunk_log, g.ctw, W, t->kw, tlo, thi, t->lb, g.tw_shift, xp, fz);
-    else ZKR_LAUNCH(ctx, (k_ntt_pass<false, (MODE == 2 || MODE == 3) ? 0 : MODE>), g.blocks, threads, smem, st, data, g.k, g.c, g.s,
-                    g.ls, g.chunk_log, g.ctw, W, t->kw, tlo, thi, t->lb, g.tw_shift, xp, fz);
+    if (dit) {
+        ZKR_LAUNCH(ctx, (k_ntt_pass<true, MODE == 1 ? 3 : MODE, 3>), g.blocks, threads, smem, st, data, g.k, g.c, g.s,
+                   g.ls, g.chunk_log, g.ctw, W, t->kw, tlo, thi, t->lb, g.tw_shift, xp, fz);
+    } else {
+        ZKR_LAUNCH(ctx, (k_ntt_pass<false, (MODE == 2 || MODE == 3) ? 0 : MODE, 3>), g.blocks, threads, smem, st, data, g.k, g.c, g.s,
+                   g.ls, g.chunk_log, g.ctw, W, t->kw, tlo, thi, t->lb, g.tw_shift, xp, fz);
+    }
     ctx->prof_end(pid, pslot, st);
     return ZKR_OK;
 }

@@ -475,7 +475,11 @@ static int prove_enqueue(zkr_ctx* ctx, const zkr_pkey* pk, char* d_proof, bool t
     ZKR_LAUNCH(ctx, k_prep_scalars, 1, 1, 0, us, wext, n, (const Fr*)pk->rs_dev, pk->err);
     ZKR_LAUNCH(ctx, k_witness_range, ceil_div(n, 256), 256, 0, us, wext, n, pk->err);
     const bool par = !ctx->serial;
-    if (par) ZKR_TRY(ctx->fork(5));
+    // ZKR_H_SPLIT=1 (experiment knob): the hExps MSM runs on its own stream (s[5]) behind the NTT pipeline (s[0]), so the
+    // two parts of the H chain can be given different stream priorities (ZKR_STREAM_PRIO)
+    static const bool h_split = getenv("ZKR_H_SPLIT") && atoi(getenv("ZKR_H_SPLIT")) != 0;
+    const int n_fork = (par && h_split) ? 6 : 5;
+    if (par) ZKR_TRY(ctx->fork(n_fork));
     cudaStream_t sH = par ? ctx->s[0] : us, sA = par ? ctx->s[1] : us, sB1 = par ? ctx->s[2] : us,
                  sB2 = par ? ctx->s[3] : us, sC = par ? ctx->s[4] : us;
     const uint32_t* w = (const uint32_t*)wext;
@@ -511,9 +515,15 @@ static int prove_enqueue(zkr_ctx* ctx, const zkr_pkey* pk, char* d_proof, bool t
     if (timed) cudaEventRecord(ev[7], sB2);
     // H chain
     if (!(h_first && par)) ZKR_TRY(h_front());
-    ZKR_TRY(delayed('H', sH));
-    ZKR_TRY(msm_run_g1(ctx, sH, pk->H, (const uint32_t*)(pk->h + pk->h_lo), pk->res + R_H, nullptr, nullptr, nullptr, late('h')));
-    if (timed) cudaEventRecord(ev[3], sH);
+    cudaStream_t sHm = sH;
+    if (par && h_split) {
+        sHm = ctx->s[5];
+        ZKR_CUDA(cudaEventRecord(ctx->ev_join[6], sH));
+        ZKR_CUDA(cudaStreamWaitEvent(sHm, ctx->ev_join[6], 0));
+    }
+    ZKR_TRY(delayed('H', sHm));
+    ZKR_TRY(msm_run_g1(ctx, sHm, pk->H, (const uint32_t*)(pk->h + pk->h_lo), pk->res + R_H, nullptr, nullptr, nullptr, late('h')));
+    if (timed) cudaEventRecord(ev[3], sHm);
     // A, then s * pi_a
     if (timed) cudaEventRecord(ev[4], sA);
     ZKR_TRY(delayed('A', sA));
@@ -535,7 +545,7 @@ static int prove_enqueue(zkr_ctx* ctx, const zkr_pkey* pk, char* d_proof, bool t
     if (comm && comm->world > 1) {
         // sharded: the five results are partial sums over this rank's point ranges.  Store them into every
         // peer's gather slot, add the `world` partials, then blind (s*pi_a, r*pib1 need the full A, B1).
-        if (par) ZKR_TRY(ctx->join(5));
+        if (par) ZKR_TRY(ctx->join(n_fork));
         int parity = 0;
         ZKR_TRY(comm_allgather_small(comm, us, pk->res, R_TOTAL, &parity));
         ZKR_LAUNCH(ctx, k_sum_res, 5, 1, 0, us, comm_gather_slot(comm, comm->rank, parity, 0), comm->world, pk->res);
@@ -547,7 +557,7 @@ static int prove_enqueue(zkr_ctx* ctx, const zkr_pkey* pk, char* d_proof, bool t
             ZKR_CUDA(cudaStreamWaitEvent(sA, ctx->ev_join[2], 0));
         }
         ZKR_LAUNCH(ctx, k_blind_muls, 2, 32 * kBlindWarps, kBlindSmem, sA, pk->res, wext, n);
-        if (par) ZKR_TRY(ctx->join(5));
+        if (par) ZKR_TRY(ctx->join(n_fork));
     }
     if (timed) cudaEventRecord(ev[12], us);
     static const int finish_fermat = getenv("ZKR_FINISH_FERMAT") ? atoi(getenv("ZKR_FINISH_FERMAT")) : 0;   // experiment knob

@@ -111,6 +111,72 @@ __global__ void k_bench_madd(uint32_t* out, int iters) {
     if (acc.x.v[0] == 0x12345678u && acc.zz.v[7] == 1) out[0] = acc.y.v[3];
 }
 
+// ---- what would batched-affine bucket accumulation cost?  (measure, do not cost on paper)
+// 8: Fermat inversions (a^(q-2), ~380 dependent modmuls), every thread of a full grid its own value
+__global__ void k_bench_inv_fermat(uint32_t* out, int iters) {
+    Fq a = Fq::one().dbl();
+    a.v[0] += threadIdx.x + blockIdx.x * 7u;
+    for (int it = 0; it < iters; it++) a = a.inverse() + Fq::one();
+    if (a.v[0] == 0x12345678u && a.v[7] == 1) out[0] = a.v[3];
+}
+// 9: the binary extended Euclid of fp_inv.cuh (no multiplier, data-dependent loops) on a full grid: the lanes of a warp
+// diverge, which is why the library only uses it on single-thread tails
+__global__ void k_bench_inv_euclid(uint32_t* out, int iters) {
+    Fq a = Fq::one().dbl();
+    a.v[0] += threadIdx.x * 2654435761u + blockIdx.x * 7u;
+    for (int it = 0; it < iters; it++) a = a.inverse_vartime() + Fq::one();
+    if (a.v[0] == 0x12345678u && a.v[7] == 1) out[0] = a.v[3];
+}
+// 10: affine + affine with Montgomery's trick over a THREAD-LOCAL batch of B pairs (the denominators' prefix products in
+// shared memory, one Fermat inversion per thread and batch): lambda = (y2 - y1) / (x2 - x1), x3 = lambda^2 - x1 - x2,
+// y3 = lambda (x1 - x3) - y1 = 5 multiplications + 1 squaring per addition + 1 inversion per batch.  Operands are
+// re-derived in registers (no table gathers): this is the arithmetic ceiling of the scheme, to be compared with
+// which = 3 (XYZZ mixed additions) at equal thread counts.
+template <int B>
+__global__ void k_bench_batch_affine(uint32_t* out, int iters) {
+    extern __shared__ uint32_t bsm[];
+    uint32_t* pre = bsm + threadIdx.x;                  // [B][8][blockDim.x] words, word-major: conflict free
+    const int stride = blockDim.x;
+    G1Affine g;
+    g.x = Fq::one();
+    g.y = Fq::one().dbl();
+    G1Affine p = XYZZ<Fq>::dbl_affine(g).to_affine();   // 2G
+    p.x.v[0] ^= 0;                                       // same point in every thread: the arithmetic does not care
+    Fq chk = Fq::zero();
+    for (int it = 0; it < iters; it++) {
+        // forward: d_i = x(Q_i) - x(P_i) with P_i = p, Q_i = (x(p) + i + 1, ...) stand-ins; prefix products
+        Fq acc = Fq::one();
+#pragma unroll 1
+        for (int i = 0; i < B; i++) {
+            Fq qx = p.x;
+            qx.v[0] += (uint32_t)(i + 1 + it);
+            const Fq d = qx - p.x;
+#pragma unroll
+            for (int l = 0; l < 8; l++) pre[(i * 8 + l) * stride] = acc.v[l];
+            acc = acc * d;
+        }
+        Fq inv = acc.inverse();
+        // backward: 1/d_i = inv * pre_i; inv *= d_i; then the addition itself
+#pragma unroll 1
+        for (int i = B - 1; i >= 0; i--) {
+            Fq qx = p.x, qy = p.y;
+            qx.v[0] += (uint32_t)(i + 1 + it);
+            qy.v[1] ^= (uint32_t)i;
+            const Fq d = qx - p.x;
+            Fq pi;
+#pragma unroll
+            for (int l = 0; l < 8; l++) pi.v[l] = pre[(i * 8 + l) * stride];
+            const Fq di = inv * pi;
+            inv = inv * d;
+            const Fq lam = (qy - p.y) * di;
+            const Fq x3 = lam.sqr() - p.x - qx;
+            const Fq y3 = lam * (p.x - x3) - p.y;
+            chk = chk + x3 + y3;
+        }
+    }
+    if (chk.v[0] == 0x12345678u && chk.v[7] == 1) out[0] = chk.v[3];
+}
+
 // FP64 pipe probes (B200 keeps the full-rate FP64 unit): can DFMA carry part of the limb products?
 __global__ void k_bench_dfma(uint32_t* out, int iters, double a, double b) {
     double x[8];
@@ -245,7 +311,7 @@ extern "C" int zkr_test_curve_op(zkr_ctx* ctx, int group, int op, const void* p,
 }
 
 extern "C" int zkr_microbench(zkr_ctx* ctx, int which, int iters, double* ops_per_s, float* ms_out) {
-    if (!ctx || which < 0 || which > 7 || iters <= 0 || !ops_per_s) return ZKR_E_INVALID;
+    if (!ctx || which < 0 || which > 11 || iters <= 0 || !ops_per_s) return ZKR_E_INVALID;
     DeviceGuard g(ctx->device);
     uint32_t* dout = nullptr;
     ZKR_CUDA(cudaMalloc(&dout, 64));
@@ -273,8 +339,22 @@ extern "C" int zkr_microbench(zkr_ctx* ctx, int which, int iters, double* ops_pe
                 per_thread = 16.0 * iters; break;          // pairs (1 DFMA + 1 IMAD.WIDE)
             case 6: ZKR_LAUNCH(ctx, k_bench_dfma_iadd, blocks, threads, 0, ctx->s[0], dout, iters, 1.0000001, 0.5);
                 per_thread = 16.0 * iters; break;          // pairs (1 DFMA + 1 64-bit add)
-            default: ZKR_LAUNCH(ctx, k_bench_iadd64, blocks, threads, 0, ctx->s[0], dout, iters, 0x123456789abcdefull);
+            case 7: ZKR_LAUNCH(ctx, k_bench_iadd64, blocks, threads, 0, ctx->s[0], dout, iters, 0x123456789abcdefull);
                 per_thread = 32.0 * iters; break;
+            case 8: ZKR_LAUNCH(ctx, k_bench_inv_fermat, blocks, threads, 0, ctx->s[0], dout, iters);
+                per_thread = 1.0 * iters; break;           // inversions
+            case 9: ZKR_LAUNCH(ctx, k_bench_inv_euclid, blocks, threads, 0, ctx->s[0], dout, iters);
+                per_thread = 1.0 * iters; break;
+            case 10: {                                      // batched affine additions, B = 16 per inversion, 128-thread CTAs
+                ZKR_CUDA(cudaFuncSetAttribute(k_bench_batch_affine<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 32 * 128));
+                ZKR_LAUNCH(ctx, k_bench_batch_affine<16>, ctx->sm_count * 3, 128, 16 * 32 * 128, ctx->s[0], dout, iters);
+                per_thread = 16.0 * iters * (ctx->sm_count * 3.0 * 128) / ((double)threads * blocks); break;
+            }
+            default: {                                      // 11: B = 64 per inversion, 64-thread CTAs
+                ZKR_CUDA(cudaFuncSetAttribute(k_bench_batch_affine<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 32 * 64));
+                ZKR_LAUNCH(ctx, k_bench_batch_affine<64>, ctx->sm_count, 64, 64 * 32 * 64, ctx->s[0], dout, iters);
+                per_thread = 64.0 * iters * (ctx->sm_count * 64.0) / ((double)threads * blocks); break;
+            }
         }
         ZKR_CUDA(cudaEventRecord(e1, ctx->s[0]));
         ZKR_CUDA(cudaEventSynchronize(e1));

@@ -16,13 +16,20 @@ res = {}
 for name, which, iters in (("imad_per_s", 0, 100000), ("imad_wide_per_s", 1, 100000),
                            ("fq_modmul_per_s", 2, 20000), ("g1_madd_per_s", 3, 3000),
                            ("dfma_per_s", 4, 100000), ("dfma_imadw_pairs_per_s", 5, 100000),
-                           ("dfma_iadd64_pairs_per_s", 6, 100000), ("iadd64_per_s", 7, 100000)):
+                           ("dfma_iadd64_pairs_per_s", 6, 100000), ("iadd64_per_s", 7, 100000),
+                           ("fq_inverse_fermat_per_s", 8, 40), ("fq_inverse_euclid_full_grid_per_s", 9, 40),
+                           ("g1_batch_affine_add_b16_per_s", 10, 60), ("g1_batch_affine_add_b64_per_s", 11, 30)):
     ops, ms = C.c_double(), C.c_float()
     _lib.check(L.zkr_microbench(h, which, iters, C.byref(ops), C.byref(ms)))
     res[name] = ops.value
     res[name.replace("_per_s", "_ms")] = ms.value
 res["modmul_imad_equiv_per_s"] = res["fq_modmul_per_s"] * 136
 res["madd_modmul_equiv_per_s"] = res["g1_madd_per_s"] * 10
+# batched affine: what one inversion costs in modmuls, and additions/s of the scheme against XYZZ mixed additions
+res["fermat_inverse_in_modmuls"] = res["fq_modmul_per_s"] / res["fq_inverse_fermat_per_s"]
+res["euclid_inverse_in_modmuls_full_grid"] = res["fq_modmul_per_s"] / res["fq_inverse_euclid_full_grid_per_s"]
+res["batch_affine_b16_vs_madd"] = res["g1_batch_affine_add_b16_per_s"] / res["g1_madd_per_s"]
+res["batch_affine_b64_vs_madd"] = res["g1_batch_affine_add_b64_per_s"] / res["g1_madd_per_s"]
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(res, open("gpurun_out/microbench.json", "w"), indent=1)
 print(json.dumps(res))
