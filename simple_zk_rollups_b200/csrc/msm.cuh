@@ -42,6 +42,10 @@ inline int level_log(size_t cnt) {
     return cnt >= kLevelBigMin ? big : kLevelLog;
 }
 constexpr uint32_t kNegBit = 0x80000000u;
+// Zero digits contribute nothing.  They used to carry their own sort key (2^(c-1), one more key bit); now they are
+// entries of bucket 0 whose value says "skip": the keys of a c-bit window fit c - 1 bits, which at c = 17 (2^18 .. 2^20
+// points, the rollup sizes) is two 8-bit radix passes instead of three.
+constexpr uint32_t kSkipVal = 0xffffffffu;
 
 struct MsmPlan {
     int c = 0, W = 0;
@@ -84,7 +88,7 @@ __global__ void k_precompute(const char* __restrict__ pts, char* __restrict__ ta
     }
 }
 
-// keys[w n + i] = |digit| - 1 (or sentinel for 0), vals[w n + i] = (w n + i) | sign
+// keys[w n + i] = |digit| - 1, vals[w n + i] = (w n + i) | sign;  digit 0 -> key 0, val kSkipVal
 static __global__ void k_digits(const uint32_t* __restrict__ scalars, const uint32_t* __restrict__ src_index, uint32_t n,
                          int c, int W, uint32_t sentinel, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
                          int* __restrict__ range_err) {
@@ -111,8 +115,8 @@ static __global__ void k_digits(const uint32_t* __restrict__ scalars, const uint
             carry = 1;
         }
         uint32_t pos = (uint32_t)w * n + i;
-        keys[pos] = d ? d - 1 : sentinel;
-        vals[pos] = pos | neg;
+        keys[pos] = d ? d - 1 : 0;
+        vals[pos] = d ? (pos | neg) : kSkipVal;
     }
 }
 
@@ -165,16 +169,18 @@ k_accum_affine(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ v
             if (p0 > 0 && prevk < sentinel) run_hi[prevk] = p0;
         }
     }
-    if (PREFETCH && have) nxt = Affine<F>::load_ro(table + AB * (size_t)(mv[0] & ~kNegBit));
+    // a skip entry (zero digit) loads table entry 0 and is not added
+    auto tab_index = [](uint32_t v) { return v == kSkipVal ? (size_t)0 : (size_t)(v & ~kNegBit); };
+    if (PREFETCH && have) nxt = Affine<F>::load_ro(table + AB * tab_index(mv[0]));
     int j = 0;                                       // after the loop: the chunk's first unprocessed entry (a sentinel) or L
     for (; j < L; j++) {
         if (!have) break;
         const uint32_t key = mk[j], v = mv[j];
         Affine<F> p;
         if (PREFETCH) p = nxt;
-        else p = Affine<F>::load_ro(table + AB * (size_t)(v & ~kNegBit));
+        else p = Affine<F>::load_ro(table + AB * tab_index(v));
         have = (j + 1 < L) && (mk[j + 1] < sentinel);
-        if (PREFETCH && have) nxt = Affine<F>::load_ro(table + AB * (size_t)(mv[j + 1] & ~kNegBit));
+        if (PREFETCH && have) nxt = Affine<F>::load_ro(table + AB * tab_index(mv[j + 1]));
         if (key != cur) {
             if (run_lo) {
                 run_hi[cur] = p0 + j;
@@ -190,8 +196,10 @@ k_accum_affine(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ v
             acc = XYZZ<F>::identity();
             cur = key;
         }
-        if (v & kNegBit) p.y = p.y.neg();
-        acc.madd(p);
+        if (v != kSkipVal) {
+            if (v & kNegBit) p.y = p.y.neg();
+            acc.madd(p);
+        }
     }
     if (cur < sentinel) {
         if (first_run) {
@@ -683,7 +691,7 @@ int bases_build(zkr_ctx* ctx, zkr_bases* b, const char* h_points, size_t n_src, 
         wk.bytes += 8 * total;
     }
     cub::DoubleBuffer<uint32_t> dk(wk.keys[0], wk.keys[1]), dv(wk.vals[0], wk.vals[1]);
-    ZKR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, wk.cub_bytes, dk, dv, (int)total, 0, b->plan.c, st));
+    ZKR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, wk.cub_bytes, dk, dv, (int)total, 0, b->plan.c > 1 ? b->plan.c - 1 : 1, st));
     ZKR_CUDA(cudaMalloc(&wk.cub_tmp, wk.cub_bytes ? wk.cub_bytes : 1));
     ZKR_CUDA(cudaMalloc(&wk.buckets, XB * (size_t)b->plan.nbuckets));
     const size_t bnd0 = 2 * (size_t)b->T1p;
@@ -746,7 +754,7 @@ int msm_run(zkr_ctx* ctx, cudaStream_t st, const zkr_bases* b, const uint32_t* d
                    wk.vals[0], wk.range_err);
         cub::DoubleBuffer<uint32_t> dk(wk.keys[0], wk.keys[1]), dv(wk.vals[0], wk.vals[1]);
         size_t tmp = wk.cub_bytes;
-        ZKR_CUDA(cub::DeviceRadixSort::SortPairs(wk.cub_tmp, tmp, dk, dv, (int)total, 0, c, st));
+        ZKR_CUDA(cub::DeviceRadixSort::SortPairs(wk.cub_tmp, tmp, dk, dv, (int)total, 0, c > 1 ? c - 1 : 1, st));
         ctx->launches += 4;   // CUB: histogram + onesweep passes (not this library's own kernels, counted as a block)
         skeys = wk.sorted_keys = dk.Current();
         svals = wk.sorted_vals = dv.Current();
