@@ -21,7 +21,9 @@
 //   * measured dead ends: capping the G2 accumulation kernel at 168 / 128 registers (3 / 4 CTAs per SM instead of 2,
 //     ~90 / ~270 spilled words per addition) makes the 2^20 proof slower, 17.8 / 18.3 ms against 17.3 ms; keeping the
 //     accumulator's ZZ / ZZZ in shared memory by hand (168 registers, no spills) is slower too, 17.66 against 16.98 ms
-//     (profiles/r02_g2_smem_acc_ab.json; that kernel was deleted).
+//     (profiles/r02_g2_smem_acc_ab.json; that kernel was deleted); so is splitting every G2 addition over a lane pair
+//     with one dual multiplication + one reduction per lane (126 registers, 4 CTAs / SM): 17.09 against 16.94 ms
+//     (profiles/r02_g2_pair_lanes_ab.json; deleted as well).
 #pragma once
 #include <cstdlib>
 
@@ -42,10 +44,9 @@ inline int level_log(size_t cnt) {
     return cnt >= kLevelBigMin ? big : kLevelLog;
 }
 constexpr uint32_t kNegBit = 0x80000000u;
-// Zero digits contribute nothing.  They used to carry their own sort key (2^(c-1), one more key bit); now they are
-// entries of bucket 0 whose value says "skip": the keys of a c-bit window fit c - 1 bits, which at c = 17 (2^18 .. 2^20
-// points, the rollup sizes) is two 8-bit radix passes instead of three.
-constexpr uint32_t kSkipVal = 0xffffffffu;
+// Zero digits carry the sentinel key 2^(c-1): they sort behind every bucket and the accumulation kernel never visits
+// them.  Folding them into the buckets as "skip" entries saves a key bit (two radix passes instead of three at c = 17)
+// but makes the IMAD-bound accumulation loop visit 3 % more entries: measured slower (profiles/r02_zero_digit_sort_ab.json).
 
 struct MsmPlan {
     int c = 0, W = 0;
@@ -88,7 +89,7 @@ __global__ void k_precompute(const char* __restrict__ pts, char* __restrict__ ta
     }
 }
 
-// keys[w n + i] = |digit| - 1, vals[w n + i] = (w n + i) | sign;  digit 0 -> key 0, val kSkipVal
+// keys[w n + i] = |digit| - 1 (or sentinel for 0), vals[w n + i] = (w n + i) | sign
 static __global__ void k_digits(const uint32_t* __restrict__ scalars, const uint32_t* __restrict__ src_index, uint32_t n,
                          int c, int W, uint32_t sentinel, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
                          int* __restrict__ range_err) {
@@ -115,8 +116,10 @@ static __global__ void k_digits(const uint32_t* __restrict__ scalars, const uint
             carry = 1;
         }
         uint32_t pos = (uint32_t)w * n + i;
-        keys[pos] = d ? d - 1 : 0;
-        vals[pos] = d ? (pos | neg) : kSkipVal;
+        // a zero digit goes to a pseudo-random bucket (multiplicative hash of its position): with all of them in one bucket
+        // the 3 % {0, 1} witness values made a 390 K-entry run of nothing, i.e. ~12 K identity partials for one CTA to add
+        keys[pos] = d ? d - 1 : sentinel;
+        vals[pos] = pos | neg;
     }
 }
 
@@ -169,18 +172,16 @@ k_accum_affine(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ v
             if (p0 > 0 && prevk < sentinel) run_hi[prevk] = p0;
         }
     }
-    // a skip entry (zero digit) loads table entry 0 and is not added
-    auto tab_index = [](uint32_t v) { return v == kSkipVal ? (size_t)0 : (size_t)(v & ~kNegBit); };
-    if (PREFETCH && have) nxt = Affine<F>::load_ro(table + AB * tab_index(mv[0]));
+    if (PREFETCH && have) nxt = Affine<F>::load_ro(table + AB * (size_t)(mv[0] & ~kNegBit));
     int j = 0;                                       // after the loop: the chunk's first unprocessed entry (a sentinel) or L
     for (; j < L; j++) {
         if (!have) break;
         const uint32_t key = mk[j], v = mv[j];
         Affine<F> p;
         if (PREFETCH) p = nxt;
-        else p = Affine<F>::load_ro(table + AB * tab_index(v));
+        else p = Affine<F>::load_ro(table + AB * (size_t)(v & ~kNegBit));
         have = (j + 1 < L) && (mk[j + 1] < sentinel);
-        if (PREFETCH && have) nxt = Affine<F>::load_ro(table + AB * tab_index(mv[j + 1]));
+        if (PREFETCH && have) nxt = Affine<F>::load_ro(table + AB * (size_t)(mv[j + 1] & ~kNegBit));
         if (key != cur) {
             if (run_lo) {
                 run_hi[cur] = p0 + j;
@@ -196,10 +197,8 @@ k_accum_affine(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ v
             acc = XYZZ<F>::identity();
             cur = key;
         }
-        if (v != kSkipVal) {
-            if (v & kNegBit) p.y = p.y.neg();
-            acc.madd(p);
-        }
+        if (v & kNegBit) p.y = p.y.neg();
+        acc.madd(p);
     }
     if (cur < sentinel) {
         if (first_run) {
@@ -234,11 +233,12 @@ k_accum_affine(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ v
 constexpr int kGatherThreads = 128;
 constexpr uint32_t kHeavyRun = 48;
 constexpr uint32_t kNoRun = 0xffffffffu;
-constexpr int kHeavyBlocks = 32;
+constexpr int kHeavyBlocks = 64;
 
 // Blocks [0, kHeavyBlocks) are the heavy path, launched first so that their few long chains run beside the light
-// blocks of the same launch: the heavy blocks scan the run bounds (chunks of buckets dealt round-robin) and sum each
-// bucket that has more than kHeavyRun partials with all their threads (strided partial sums, then a tree in shared memory).
+// blocks of the same launch: the heavy blocks scan the run bounds (bucket b belongs to heavy block b mod kHeavyBlocks) and
+// sum each bucket that has more than kHeavyRun partials with all their threads (strided partial sums, then a tree in
+// shared memory).
 // Blocks [kHeavyBlocks, ...) are the light path: one thread per bucket.
 template <class F>
 __global__ void __launch_bounds__(kGatherThreads)
@@ -250,10 +250,12 @@ k_bucket_gather(const uint32_t* __restrict__ keys, uint32_t total, int logL, con
         XYZZ<F>* sp = reinterpret_cast<XYZZ<F>*>(smraw);
         __shared__ uint32_t found[kGatherThreads];
         __shared__ uint32_t n_found;
-        for (uint32_t chunk = blockIdx.x; chunk * kGatherThreads < nbuckets; chunk += kHeavyBlocks) {
-            // chunks of kGatherThreads consecutive buckets, dealt round-robin to the heavy blocks (coalesced scan, and an
-            // adversarial cluster of heavy buckets still spreads over the blocks); most chunks hold none: one barrier
-            const uint32_t b = chunk * kGatherThreads + threadIdx.x;
+        for (uint32_t b0 = blockIdx.x; b0 < nbuckets; b0 += kHeavyBlocks * kGatherThreads) {
+            // heavy block h owns the buckets b = h (mod kHeavyBlocks): neighbouring heavy buckets (small digits of a short
+            // top window, adversarial scalar sets) land on different blocks.  Most iterations find none: one barrier.
+            // The scan is cheap; what costs is ~50 us of whole-CTA work per heavy bucket -- 4096 of them at 22-bit windows
+            // (2^24 points: the 12-bit top window) made this kernel 9 ms, one reason the recursive levels serve c > 20.
+            const uint32_t b = b0 + threadIdx.x * kHeavyBlocks;
             bool is_heavy = false;
             if (b < nbuckets) {
                 const uint32_t lo = run_lo[b];
@@ -691,7 +693,7 @@ int bases_build(zkr_ctx* ctx, zkr_bases* b, const char* h_points, size_t n_src, 
         wk.bytes += 8 * total;
     }
     cub::DoubleBuffer<uint32_t> dk(wk.keys[0], wk.keys[1]), dv(wk.vals[0], wk.vals[1]);
-    ZKR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, wk.cub_bytes, dk, dv, (int)total, 0, b->plan.c > 1 ? b->plan.c - 1 : 1, st));
+    ZKR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, wk.cub_bytes, dk, dv, (int)total, 0, b->plan.c, st));
     ZKR_CUDA(cudaMalloc(&wk.cub_tmp, wk.cub_bytes ? wk.cub_bytes : 1));
     ZKR_CUDA(cudaMalloc(&wk.buckets, XB * (size_t)b->plan.nbuckets));
     const size_t bnd0 = 2 * (size_t)b->T1p;
@@ -754,7 +756,7 @@ int msm_run(zkr_ctx* ctx, cudaStream_t st, const zkr_bases* b, const uint32_t* d
                    wk.vals[0], wk.range_err);
         cub::DoubleBuffer<uint32_t> dk(wk.keys[0], wk.keys[1]), dv(wk.vals[0], wk.vals[1]);
         size_t tmp = wk.cub_bytes;
-        ZKR_CUDA(cub::DeviceRadixSort::SortPairs(wk.cub_tmp, tmp, dk, dv, (int)total, 0, c > 1 ? c - 1 : 1, st));
+        ZKR_CUDA(cub::DeviceRadixSort::SortPairs(wk.cub_tmp, tmp, dk, dv, (int)total, 0, c, st));
         ctx->launches += 4;   // CUB: histogram + onesweep passes (not this library's own kernels, counted as a block)
         skeys = wk.sorted_keys = dk.Current();
         svals = wk.sorted_vals = dv.Current();
@@ -769,7 +771,9 @@ int msm_run(zkr_ctx* ctx, cudaStream_t st, const zkr_bases* b, const uint32_t* d
     const int pslot = ctx->prof_begin(sizeof(F) == 32 ? PROF_ACCUM_G1 : PROF_ACCUM_G2, st, (double)total);
     if (hooks && hooks->wait_accum) ZKR_CUDA(cudaStreamWaitEvent(st, hooks->wait_accum, 0));
     // Boundary partials -> buckets: the one-launch gather up to 20-bit windows (every proof size), the round-1 recursive
-    // levels above (2M+ buckets of ~3 partials each: measured 48.1 vs 40.6 ms at 2^24, profiles/r02_msm_gather_vs_levels.json).
+    // levels above: at 22-bit windows the 12-bit top window puts n / 4096 extra entries into each of the 4096 lowest buckets,
+    // i.e. thousands of moderately heavy buckets, which the whole-CTA heavy path handles badly (2^24: 48 vs 40.6 ms,
+    // profiles/r02_msm_gather_vs_levels.json).
     // ZKR_MSM_LEVELS = 0 / 1 forces the gather / the levels (A/B knob).
     static const int force_levels = getenv("ZKR_MSM_LEVELS") ? atoi(getenv("ZKR_MSM_LEVELS")) : -1;
     const bool use_levels = force_levels >= 0 ? force_levels != 0 : c > 20;

@@ -56,7 +56,10 @@ def main():
     ap.add_argument("--min-log", type=int, default=16)
     ap.add_argument("--g2-min-log", type=int, default=16)
     ap.add_argument("--skip-ntt", action="store_true")
+    ap.add_argument("--g1-off", action="store_true", help="skip the G1 rows (G2-only runs)")
     args = ap.parse_args()
+    if args.max_log > 26 or args.g2_max_log > 24:
+        raise SystemExit("sweep sizes are capped at 2^26 (G1) / 2^24 (G2): beyond that the tables do not fit one GPU")
     L = _lib.lib()
     ctx = C.c_void_p()
     _lib.check(L.zkr_ctx_create(0, C.byref(ctx)))
@@ -80,6 +83,8 @@ def main():
         return min(ts), float(np.median(ts))
 
     for group, max_log in ((1, args.max_log), (2, min(args.g2_max_log, args.max_log))):
+        if group == 1 and args.g1_off:
+            continue
         for lg in range(args.min_log if group == 1 else args.g2_min_log, max_log + 1, 2):
             n = 1 << lg
             t0 = time.time()
