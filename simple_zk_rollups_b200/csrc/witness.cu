@@ -16,9 +16,11 @@
 //
 // Build (once per circuit, host): CSC-by-signal -> CSR-by-row, the defined signal of every row, its level in the
 // dependency graph (1 + the deepest operand), operations sorted by level.  Solve (per proof, device): scatter the given
-// values, then one launch per level -- all Feistel chains advance one step per launch -- with the witness left resident
+// values, then walk the levels -- all Feistel chains advance one step per level -- in ONE persistent launch with a grid
+// barrier between levels (one launch per level is kept behind ZKR_WITNESS_PER_LEVEL=1), with the witness left resident
 // in HBM in the layout zkr_prove_dev takes (n x 32 B, standard form): no 27 MB host round trip per proof.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -36,6 +38,8 @@ struct zkr_wprog {
     uint32_t *ptr[3] = {}, *sig[3] = {}, *cid[3] = {};   // CSR by row of A, B, C
     uint32_t *op_row = nullptr, *op_out = nullptr, *op_kcid = nullptr;   // sorted by level
     uint32_t* d_given = nullptr;
+    uint32_t* d_level_ofs = nullptr;
+    unsigned int* bar = nullptr;
     Fr *pool = nullptr, *pool_inv = nullptr;              // Montgomery form
     Fr* given_vals = nullptr;                              // staging, n_given
     int* err = nullptr;
@@ -69,9 +73,61 @@ __device__ __forceinline__ Fr row_lc(const uint32_t* __restrict__ ptr, const uin
     for (uint32_t k = ptr[row]; k < e; k++) {
         const uint32_t s = sig[k];
         if (s == skip) continue;
-        acc = acc + Fr::load(w + s) * Fr::load_ro(pool + cid[k]);     // standard x Montgomery -> standard
+        // w is written by other CTAs of the same launch (persistent solve): read it through L2, never a stale L1 line
+        const uint4* q = reinterpret_cast<const uint4*>(w + s);
+        const uint4 x0 = __ldcg(q), x1 = __ldcg(q + 1);
+        Fr ws;
+        ws.v[0] = x0.x; ws.v[1] = x0.y; ws.v[2] = x0.z; ws.v[3] = x0.w;
+        ws.v[4] = x1.x; ws.v[5] = x1.y; ws.v[6] = x1.z; ws.v[7] = x1.w;
+        acc = acc + ws * Fr::load_ro(pool + cid[k]);     // standard x Montgomery -> standard
     }
     return acc;
+}
+
+struct SolveArgs {
+    const uint32_t *op_row, *op_out, *op_kcid, *level_ofs;
+    const uint32_t *pa, *sa, *ca, *pb, *sb, *cb, *pc, *sc, *cc;
+    const Fr *pool, *pool_inv;
+    Fr* w;
+    uint32_t n_levels;
+    unsigned int* bar;     // grid barrier counter (zeroed before the launch)
+    int* err;
+};
+
+// ALL levels in one launch: a persistent grid of one CTA per SM walks the levels, a counter barrier in global memory
+// between them (every CTA is resident: the grid is never larger than the SM count, the kernel uses no shared memory and
+// few registers).  663 launches of ~11 us each (launch latency + one dependent-load chain) become 663 barriers of ~3 us.
+// The spin is bounded (2 s): a CTA that cannot see its peers sets the error flag instead of hanging the GPU.
+__global__ void __launch_bounds__(128) k_solve_all(SolveArgs a) {
+    const unsigned nblk = gridDim.x;
+    for (uint32_t l = 0; l < a.n_levels; l++) {
+        const uint32_t lo = a.level_ofs[l], hi = a.level_ofs[l + 1];
+        for (uint32_t i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += nblk * blockDim.x) {
+            const uint32_t row = a.op_row[i], out = a.op_out[i];
+            const Fr la = row_lc(a.pa, a.sa, a.ca, row, a.pool, a.w, 0xffffffffu);
+            const Fr lb = row_lc(a.pb, a.sb, a.cb, row, a.pool, a.w, 0xffffffffu);
+            const Fr lc = row_lc(a.pc, a.sc, a.cc, row, a.pool, a.w, out);
+            const Fr u = (la * lb).to_mont() - lc;
+            (u * Fr::load_ro(a.pool_inv + a.op_kcid[i])).store(a.w + out);
+        }
+        if (l + 1 == a.n_levels) break;
+        // grid barrier: this level's stores must be visible to every CTA before the next level reads them
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            atomicAdd(a.bar, 1u);
+            const unsigned target = (l + 1) * nblk;
+            const long long t0 = clock64();
+            while (*(volatile unsigned int*)a.bar < target) {
+                if (clock64() - t0 > 4000000000ll) {      // ~2 s at 2 GHz
+                    *a.err = 2;
+                    break;
+                }
+            }
+            __threadfence();
+        }
+        __syncthreads();
+    }
 }
 
 // one level of the dependency graph: w[out] = ((A.w)(B.w) - C'.w) / c_out
@@ -106,7 +162,7 @@ void wprog_release(zkr_wprog* p) {
         cudaFree(p->sig[m]);
         cudaFree(p->cid[m]);
     }
-    void* ps[] = {p->op_row, p->op_out, p->op_kcid, p->d_given, p->pool, p->pool_inv, p->given_vals, p->err};
+    void* ps[] = {p->op_row, p->op_out, p->op_kcid, p->d_given, p->pool, p->pool_inv, p->given_vals, p->err, p->d_level_ofs, p->bar};
     for (void* q : ps) cudaFree(q);
     delete p;
 }
@@ -240,6 +296,11 @@ extern "C" int zkr_wprog_build(zkr_ctx* ctx, const zkr_r1cs_csc* r, zkr_wprog** 
     WP_TRY(up(s_out.data(), s_out.size() * 4, (void**)&p->op_out, st, &p->bytes));
     WP_TRY(up(s_kc.data(), s_kc.size() * 4, (void**)&p->op_kcid, st, &p->bytes));
     WP_TRY(up(p->given.data(), p->given.size() * 4, (void**)&p->d_given, st, &p->bytes));
+    WP_TRY(up(p->level_ofs.data(), p->level_ofs.size() * 4, (void**)&p->d_level_ofs, st, &p->bytes));
+    if (cudaMalloc(&p->bar, sizeof(unsigned int)) != cudaSuccess) {
+        wprog_release(p);
+        return ZKR_E_NOMEM;
+    }
     WP_TRY(up(r->pool, 32 * (size_t)r->n_pool, (void**)&p->pool, st, &p->bytes));
     cudaError_t e1 = cudaMalloc(&p->pool_inv, 32 * (size_t)(r->n_pool ? r->n_pool : 1));
     cudaError_t e2 = cudaMalloc(&p->given_vals, 32 * (size_t)(p->n_given ? p->n_given : 1));
@@ -289,12 +350,33 @@ extern "C" int zkr_witness_solve(zkr_ctx* ctx, const zkr_wprog* p, const void* g
     ZKR_CUDA(cudaMemcpyAsync(p->given_vals, given_values, 32 * (size_t)p->n_given, cudaMemcpyHostToDevice, st));
     ZKR_LAUNCH(ctx, k_scatter_given, ceil_div(p->n_given, 128), 128, 0, st, (Fr*)d_witness, p->d_given, p->given_vals, p->n_given,
                p->err);
-    for (uint32_t l = 0; l < p->n_levels; l++) {
-        const uint32_t lo = p->level_ofs[l], hi = p->level_ofs[l + 1];
-        if (hi == lo) continue;
-        ZKR_LAUNCH(ctx, k_solve_level, ceil_div(hi - lo, 64), 64, 0, st, p->op_row, p->op_out, p->op_kcid, lo, hi, p->ptr[0],
-                   p->sig[0], p->cid[0], p->ptr[1], p->sig[1], p->cid[1], p->ptr[2], p->sig[2], p->cid[2], p->pool, p->pool_inv,
-                   (Fr*)d_witness);
+    // ZKR_WITNESS_PER_LEVEL=1 (A/B knob): one launch per level instead of the persistent kernel
+    const bool per_level = getenv("ZKR_WITNESS_PER_LEVEL") && atoi(getenv("ZKR_WITNESS_PER_LEVEL")) != 0;   // per call: tests toggle it
+    if (per_level) {
+        for (uint32_t l = 0; l < p->n_levels; l++) {
+            const uint32_t lo = p->level_ofs[l], hi = p->level_ofs[l + 1];
+            if (hi == lo) continue;
+            ZKR_LAUNCH(ctx, k_solve_level, ceil_div(hi - lo, 64), 64, 0, st, p->op_row, p->op_out, p->op_kcid, lo, hi, p->ptr[0],
+                       p->sig[0], p->cid[0], p->ptr[1], p->sig[1], p->cid[1], p->ptr[2], p->sig[2], p->cid[2], p->pool, p->pool_inv,
+                       (Fr*)d_witness);
+        }
+    } else if (p->n_levels) {
+        SolveArgs a;
+        a.op_row = p->op_row; a.op_out = p->op_out; a.op_kcid = p->op_kcid; a.level_ofs = p->d_level_ofs;
+        a.pa = p->ptr[0]; a.sa = p->sig[0]; a.ca = p->cid[0];
+        a.pb = p->ptr[1]; a.sb = p->sig[1]; a.cb = p->cid[1];
+        a.pc = p->ptr[2]; a.sc = p->sig[2]; a.cc = p->cid[2];
+        a.pool = p->pool; a.pool_inv = p->pool_inv;
+        a.w = (Fr*)d_witness;
+        a.n_levels = p->n_levels;
+        a.bar = p->bar;
+        a.err = p->err;
+        ZKR_CUDA(cudaMemsetAsync(p->bar, 0, sizeof(unsigned int), st));
+        // never more CTAs than SMs (all must be resident for the barrier); small circuits use fewer
+        uint32_t widest = 0;
+        for (uint32_t l = 0; l < p->n_levels; l++) widest = std::max(widest, p->level_ofs[l + 1] - p->level_ofs[l]);
+        const int blocks = std::max(1, std::min(ctx->sm_count, ceil_div(widest, 128)));
+        ZKR_LAUNCH(ctx, k_solve_all, blocks, 128, 0, st, a);
     }
     // the given values are host memory of the caller: they must have been read before we return; the flag rides along
     int e = 0;
@@ -302,6 +384,10 @@ extern "C" int zkr_witness_solve(zkr_ctx* ctx, const zkr_wprog* p, const void* g
     ZKR_CUDA(cudaStreamSynchronize(st));
     if (e) {
         ZKR_CUDA(cudaMemsetAsync(p->err, 0, sizeof(int), st));
+        if (e == 2) {
+            set_error("witness solve: grid barrier timed out (the persistent kernel's CTAs were not co-resident)");
+            return ZKR_E_CUDA;
+        }
         set_error("a given witness value is >= r");
         return ZKR_E_WITNESS_RANGE;
     }

@@ -52,6 +52,19 @@ def test_solver_reproduces_the_host_witness(gp, nc, npub, seed):
         ws.close()
 
 
+def test_per_level_and_persistent_solves_agree(gp, monkeypatch):
+    """ZKR_WITNESS_PER_LEVEL=1 (one launch per level) and the default persistent kernel (grid barrier between levels)."""
+    r1, w = synth.generate(2500, 6, seed=21)
+    ws = witness.WitnessSolver(gp, r1)
+    try:
+        given = ws.given_from_witness(w)
+        assert ws.solve(given) == w
+        monkeypatch.setenv("ZKR_WITNESS_PER_LEVEL", "1")
+        assert ws.solve(given) == w
+    finally:
+        ws.close()
+
+
 def test_same_circuit_different_witness_seed(gp):
     """synth.generate(witness_seed=k): same circuit, the solver must reproduce each witness from its given values."""
     r1, wa = synth.generate(900, 4, seed=5, witness_seed=1)
