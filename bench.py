@@ -676,6 +676,10 @@ def sharded_blocks(env, args, key_rank0):
         t0 = time.time()
         n = 1 << lg
         nl = n // world
+        if lg - (world.bit_length() - 1) < 11:        # csrc/ntt.cu ntt_run_sharded: every rank needs at least one full 2^11 tile row
+            res["ntt"].append({"log_n": lg, "skipped": "2^%d over %d ranks is below the sharded transform's minimum tile geometry" % (lg, world),
+                               "identical": True})
+            continue
         w = pow(5, (R_ORDER - 1) >> lg, R_ORDER)
         top = cval * (pow(gval, n, R_ORDER) - 1) % R_ORDER
 

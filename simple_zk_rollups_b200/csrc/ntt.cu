@@ -454,6 +454,22 @@ int plan_passes(int n, int* ks) {
     if (np < 1) np = 1;
     int base = n / np, rem = n % np;
     for (int i = 0; i < np; i++) ks[i] = base + (i < rem ? 1 : 0);
+    // ZKR_NTT_SPLIT="a,b[,c]" (experiment knob): explicit pass widths for transforms whose size they sum to
+    if (const char* e = getenv("ZKR_NTT_SPLIT")) {
+        int v[4], cnt = 0, sum = 0;
+        for (const char* q = e; q && *q && cnt < 4;) {
+            v[cnt] = atoi(q);
+            sum += v[cnt++];
+            q = strchr(q, ',');
+            if (q) q++;
+        }
+        bool ok = sum == n && cnt >= 1;
+        for (int i = 0; i < cnt; i++) ok = ok && v[i] >= 3 && v[i] <= kTileLog;
+        if (ok) {
+            for (int i = 0; i < cnt; i++) ks[i] = v[i];
+            np = cnt;
+        }
+    }
     return np;
 }
 

@@ -249,3 +249,89 @@ def test_prove_full_size(gp, shape):
     assert g.exponent_check_flat(mats, r1.pool, npub, w, TOXIC, m, g.proof_from_bytes(zero), 0, 0, sums=sums)
     gp.L.zkr_pkey_free(key)
     gp._keys.remove(key)
+
+
+def test_prove_dev_flags_and_prove_check(gp):
+    """zkr_prove_dev is asynchronous and cannot return ZKR_E_WITNESS_RANGE: the flags stay set until zkr_prove_check reads
+    them, and a later zkr_prove starts from clean flags (a stale flag failed the next valid proof once)."""
+    import ctypes as C
+    L = gp.L
+    r1, w = synth.generate(60, 2, seed=13)
+    pk, vk, _ = g.setup(r1.to_dicts(), TOXIC)
+    key = gp.load_key(bf.binarify_proving_key(pk))
+    n = r1.nVars
+    good = np.frombuffer(bf.binarify_witness(w), dtype=np.uint8)
+    w_bad = list(w)
+    w_bad[4] = R                                         # out of range
+    bad = np.frombuffer(bf.binarify_witness(w_bad), dtype=np.uint8)
+    d_w, d_p = C.c_void_p(), C.c_void_p()
+    _lib.check(L.zkr_dev_malloc(gp.ctx, 32 * n, C.byref(d_w)))
+    _lib.check(L.zkr_dev_malloc(gp.ctx, 256, C.byref(d_p)))
+    rb = np.frombuffer(int(5).to_bytes(32, "little"), dtype=np.uint8)
+    sb = np.frombuffer(int(6).to_bytes(32, "little"), dtype=np.uint8)
+    want = g.proof_to_bytes(g.gen_proof(pk, w, 5, 6)[0])
+    # valid input: OK and the right bytes
+    _lib.check(L.zkr_dev_upload(gp.ctx, d_w, _lib.buf_ptr(good), good.size))
+    _lib.check(L.zkr_prove_dev(gp.ctx, key, d_w, n, _lib.buf_ptr(rb), _lib.buf_ptr(sb), d_p))
+    assert L.zkr_prove_check(gp.ctx, key) == 0
+    out = np.zeros(256, dtype=np.uint8)
+    _lib.check(L.zkr_dev_download(gp.ctx, _lib.buf_ptr(out), d_p, 256))
+    assert out.tobytes() == want
+    # invalid input: the call itself succeeds, the check reports it once, then the flags are clean again
+    _lib.check(L.zkr_dev_upload(gp.ctx, d_w, _lib.buf_ptr(bad), bad.size))
+    assert L.zkr_prove_dev(gp.ctx, key, d_w, n, _lib.buf_ptr(rb), _lib.buf_ptr(sb), d_p) == 0
+    assert L.zkr_prove_check(gp.ctx, key) == -3
+    assert L.zkr_prove_check(gp.ctx, key) == 0
+    # an unchecked bad zkr_prove_dev must not fail the next blocking proof
+    assert L.zkr_prove_dev(gp.ctx, key, d_w, n, _lib.buf_ptr(rb), _lib.buf_ptr(sb), d_p) == 0
+    got, _ = gp.prove(key, good, 5, 6)
+    assert got == want
+    _lib.check(L.zkr_dev_free(gp.ctx, d_w))
+    _lib.check(L.zkr_dev_free(gp.ctx, d_p))
+
+
+def test_default_blinding_is_random_and_valid(gp):
+    """prove() without r, s (NULL at the C-ABI) draws CSPRNG scalars like websnark: two proofs of the same statement differ
+    and both verify; explicit zeros give the deterministic snarkjs debug proof."""
+    import ctypes as C
+    r1, w = synth.generate(80, 3, seed=14)
+    pk, vk, _ = g.setup(r1.to_dicts(), TOXIC)
+    key = gp.load_key(bf.binarify_proving_key(pk))
+    wb = bf.binarify_witness(w)
+    a, _ = gp.prove(key, wb)
+    b, _ = gp.prove(key, wb)
+    assert a != b
+    pub = w[1:4]
+    assert g.verify(vk, g.proof_from_bytes(a), pub) and g.verify(vk, g.proof_from_bytes(b), pub)
+    z1, _ = gp.prove(key, wb, 0, 0)
+    z2, _ = gp.prove(key, wb, 0, 0)
+    assert z1 == z2 == g.proof_to_bytes(g.gen_proof(pk, w, 0, 0)[0])
+    # NULL straight at the C-ABI
+    out1, out2 = np.zeros(256, dtype=np.uint8), np.zeros(256, dtype=np.uint8)
+    warr = np.frombuffer(wb, dtype=np.uint8)
+    for o in (out1, out2):
+        _lib.check(gp.L.zkr_prove(gp.ctx, key, _lib.buf_ptr(warr), r1.nVars, None, None, _lib.buf_ptr(o), None))
+    assert out1.tobytes() != out2.tobytes()
+    assert g.verify(vk, g.proof_from_bytes(out1.tobytes()), pub)
+
+
+def test_genproof_key_cache(gp):
+    """genProof caches the resident key per (prover, key object / key bytes): repeated calls do not load the key again,
+    a different circuit is never served a stale key."""
+    r1, w = synth.generate(40, 2, seed=15)
+    r2, w2 = synth.generate(40, 2, seed=16)
+    pk1, vk1, _ = g.setup(r1.to_dicts(), TOXIC)
+    pk2, vk2, _ = g.setup(r2.to_dicts(), TOXIC)
+    j1, j2 = bf.pk_to_json(pk1), bf.pk_to_json(pk2)
+    n0 = len(gp._keys)
+    o1 = prover.genProof(j1, w, 3, 4, prover=gp)
+    o1b = prover.genProof(j1, w, 3, 4, prover=gp)
+    assert len(gp._keys) == n0 + 1 and o1 == o1b
+    o2 = prover.genProof(j2, w2, 3, 4, prover=gp)
+    assert len(gp._keys) == n0 + 2
+    assert bf.proof_from_json(o1["proof"]) == g.gen_proof(pk1, w, 3, 4)[0]
+    assert bf.proof_from_json(o2["proof"]) == g.gen_proof(pk2, w2, 3, 4)[0]
+    b1 = bf.binarify_proving_key(pk1)
+    prover.genProof(b1, w, 3, 4, prover=gp)
+    prover.genProof(bytes(b1), w, 3, 4, prover=gp)
+    assert len(gp._keys) == n0 + 3                       # the binary form is cached by content, not reloaded per call

@@ -65,7 +65,7 @@ def main():
             ca_ = "; ".join("2^%d %.1f s" % (l, a) for l, _, _, _, a, _, _ in cells if a)
             cb_ = "; ".join("2^%d %.2f s" % (l, b) for l, _, _, _, _, b, _ in cells if b)
             ok = all(c[-1] for c in cells) and all(r["correct"] for r in sw["msm"] if r["group"] == group)
-            rows.append("| 3 | 1 | %s MSM (`r02_sweep_1gpu.json`; N > 1: `sharded.msm_g1` of the N-GPU bench lines) | %s | %s | – | %s | %s "
+            rows.append("| 3 | 1 | %s MSM (`r02_sweep_1gpu.json`) | %s | %s | – | %s | %s "
                         "| %s: every row (uniform, rollup-like, adversarial sets) equals the host-computed expectation |" % (
                             name, gpu, fr, ca_ or "–", cb_ or "–", "yes" if ok else "NO"))
         nt = [r for r in sw["ntt"] if r["op"] == "forward_dif"]
@@ -75,8 +75,26 @@ def main():
         ca_ = "; ".join("2^%d %.3f s" % (r["log_n"], r["cpu_baseline"]["cpu_a"]["seconds"]) for r in nt if "cpu_a" in r.get("cpu_baseline", {}))
         cb_ = "; ".join("2^%d %.3f s" % (r["log_n"], r["cpu_baseline"]["cpu_b"]["seconds"]) for r in nt if "cpu_b" in r.get("cpu_baseline", {}))
         ok = all(r["correct"] for r in sw["ntt"])
-        rows.append("| 4 | 1 | NTT forward (`r02_sweep_1gpu.json`; N > 1: `sharded.ntt` of the N-GPU bench lines) | %s | %s | %s | %s | %s | %s: "
+        rows.append("| 4 | 1 | NTT forward (`r02_sweep_1gpu.json`) | %s | %s | %s | %s | %s | %s: "
                     "closed-form values at 10 indices + round trip; Horner at 2^20 / 2^24 in tests |" % (gpu, fr, hb, ca_, cb_, "yes" if ok else "NO"))
+    msm_cells, ntt_cells, ok_sh = [], [], True
+    for n in (2, 4, 8):
+        d = maybe("r02_bench_n%d.json" % n)
+        if d and d.get("sharded"):
+            sh = d["sharded"]
+            ok_sh = ok_sh and sh["identical"]
+            for r in sh["msm_g1"]:
+                msm_cells.append("%d GPUs 2^%d: %.2f ms = %.2f Gpts/s (%.2fx of 1 GPU)" % (n, r["log_n"], r["ms"], r["gpts_per_s"], r["speedup_vs_1gpu"]))
+            for r in sh["ntt"]:
+                if "dif_ms" in r:
+                    ntt_cells.append("%d GPUs 2^%d: %.3f ms = %.0f GB/s aggregate (%.2fx), %.0f GB/s out per rank in the exchange pass" % (
+                        n, r["log_n"], r["dif_ms"], r["aggregate_gb_per_s"], r["speedup_vs_1gpu"], r["nvlink_gb_per_s_per_rank"]))
+    if msm_cells:
+        rows.append("| 3 | 2/4/8 | G1 MSM sharded by point range (`sharded.msm_g1` of `r02_bench_n{2,4,8}.json`) | %s | – | – | – | – | %s: host-only "
+                    "expectation, every rank |" % ("; ".join(msm_cells), "yes" if ok_sh else "NO"))
+    if ntt_cells:
+        rows.append("| 4 | 2/4/8 | four-step NTT, all-to-all fused into a pass (`sharded.ntt`) | %s | – | – | – | – | %s: closed-form values + round "
+                    "trip, every rank |" % ("; ".join(ntt_cells), "yes" if ok_sh else "NO"))
     cells = []
     for n in (1, 2, 4, 8):
         d = maybe("r02_bench_n%d.json" % n)
