@@ -297,29 +297,36 @@ def run_ours(args):
     # proofs are in flight and one proof's latency-bound tail overlaps the other's bulk kernels
     ms_batch2 = None
     if not args.no_two_in_flight:
-        gp2 = prover.Groth16Prover(local)
-        stream2 = torch.cuda.Stream()
-        _lib.check(L.zkr_ctx_set_stream(gp2.ctx, C.c_void_p(stream2.cuda_stream)))
-        key2 = gp2.load_key(pk_bin)
-        ctxs2, pks2 = (C.c_void_p * 2)(gp.ctx, gp2.ctx), (C.c_void_p * 2)(key, key2)
+        K = max(2, args.in_flight)
+        extra, streams, keys_k = [], [], []
+        for _ in range(K - 1):
+            g2_ = prover.Groth16Prover(local)
+            st_ = torch.cuda.Stream()
+            _lib.check(L.zkr_ctx_set_stream(g2_.ctx, C.c_void_p(st_.cuda_stream)))
+            extra.append(g2_)
+            streams.append(st_)
+            keys_k.append(g2_.load_key(pk_bin))
+        ctxs2 = (C.c_void_p * K)(gp.ctx, *[e_.ctx for e_ in extra])
+        pks2 = (C.c_void_p * K)(key, *keys_k)
 
         def prove_batch_host2(nproofs):
             wptrs = (C.c_void_p * nproofs)(*[(w_host if i % 2 == 0 else w_host2).data_ptr() for i in range(nproofs)])
             rsb = np.tile(rs_pair, nproofs)
             outb = np.zeros(256 * nproofs, dtype=np.uint8)
-            _lib.check(L.zkr_prove_batch(ctxs2, pks2, 2, wptrs, n, nproofs, _lib.buf_ptr(rsb), _lib.buf_ptr(outb)))
+            _lib.check(L.zkr_prove_batch(ctxs2, pks2, K, wptrs, n, nproofs, _lib.buf_ptr(rsb), _lib.buf_ptr(outb)))
             return outb
-        ob = prove_batch_host2(4)
-        assert all(ob[256 * i:256 * i + 256].tobytes() == out.tobytes() for i in range(4)), "two-in-flight proofs differ"
+        ob = prove_batch_host2(2 * K)
+        assert all(ob[256 * i:256 * i + 256].tobytes() == out.tobytes() for i in range(2 * K)), "in-flight proofs differ"
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        ob = prove_batch_host2(2 * args.steps)
+        ob = prove_batch_host2(K * args.steps)
         e1.record(stream)
         barrier()
-        ms_batch2 = max_over_ranks(e0.elapsed_time(e1)) / 2.0          # per `steps` proofs, comparable with ms_batch
-        assert all(ob[256 * i:256 * i + 256].tobytes() == out.tobytes() for i in range(2 * args.steps))
-        gp2.close()
+        ms_batch2 = max_over_ranks(e0.elapsed_time(e1)) / K            # per `steps` proofs, comparable with ms_batch
+        assert all(ob[256 * i:256 * i + 256].tobytes() == out.tobytes() for i in range(K * args.steps))
+        for e_ in extra:
+            e_.close()
     _lib.check(L.zkr_prove_check(gp.ctx, key))       # input-validity flags of the zkr_prove_dev calls above
     stage_ms = {k: round(v, 3) for k, v in stats.as_dict().items() if k.endswith("_ms")}
     ms_single_gpu_proof = ms_e2e / args.steps
@@ -507,11 +514,11 @@ def run_ours(args):
                     "d2h_bytes_per_step": 256, "ms_per_step": round(ms_e2e_step, 4),
                     "api": "zkr_prove_batch on host witness buffers (pinned): per proof H2D of the witness + (r,s), "
                            "D2H of the 256-byte proof and the range flags; witness i+1 is uploaded while proof i runs"
-                           + ("; two contexts with one key replica each per GPU = two proofs in flight" if use_two else
+                           + ("; %d contexts with one key replica each per GPU = %d proofs in flight" % (max(2, args.in_flight), max(2, args.in_flight)) if use_two else
                               "; one context per GPU = one proof in flight"),
                     "one_in_flight": {"value": round(e2e_one, 3), "ms_per_step": round(ms_batch / args.steps, 4)},
                     "two_in_flight": None if e2e_two is None else {"value": round(e2e_two, 3), "ms_per_step": round(ms_batch2 / args.steps, 4),
-                                                                   "key_replicas_per_gpu": 2},
+                                                                   "key_replicas_per_gpu": max(2, args.in_flight)},
                     "single_call": {"api": "zkr_prove (one blocking call per proof, nothing overlapped)",
                                     "value": round(world * args.steps / (ms_e2e * 1e-3), 3),
                                     "ms_per_step": round(ms_e2e / args.steps, 4)}},
@@ -1142,6 +1149,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs under ncu)")
     ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the sharded proof / NTT / MSM block")
     ap.add_argument("--no-gpu-witness", action="store_true", help="skip the witness-on-GPU block")
+    ap.add_argument("--in-flight", type=int, default=2, help="contexts / key replicas per GPU in the e2e leg (default 2)")
     ap.add_argument("--no-two-in-flight", action="store_true", help="skip the e2e leg with two contexts / key replicas per GPU")
     ap.add_argument("--no-batch-2p22", action="store_true", help="skip the BASELINE configs[4] batch block")
     ap.add_argument("--sharded-ntt-logs", default="24,26")
