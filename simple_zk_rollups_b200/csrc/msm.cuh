@@ -478,6 +478,8 @@ __device__ __forceinline__ void mul_small_mem(XYZZ<F>* p, XYZZ<F>* tmp, uint32_t
 // (measured: the overlapped proof got 0.8 ms SLOWER with 256-thread reduction CTAs although the serialised
 // one got 2.4 ms faster).  32 threads x up to 255 registers leave the SM to the accumulation kernels.
 constexpr int kReduceThreads = 32;
+// (256-thread CTAs for small MSMs -- one element per thread, 8 tree levels -- were timed in round 2 and are slower
+// everywhere: profiles/r02_reduce_width_ab.json.)
 
 // Bucket reduction  sum_b (b+1) B_b  without a serial running sum.  Split b = hi * 2^lc + lo:
 //     sum_b b B_b = 2^lc * sum_hi hi * Row[hi]  +  sum_lo lo * Col[lo],      sum_b B_b = sum_hi Row[hi]
@@ -488,8 +490,8 @@ constexpr int kReduceThreads = 32;
 // latency of the reduction is ~2 tree depths + (c-2) doublings instead of thousands of chained additions.
 
 // stage 1: CTA g < 2^lr: Row[g];  CTA 2^lr + l: Col[l]
-template <class F>
-__global__ void __launch_bounds__(kReduceThreads)
+template <class F, int NT>
+__global__ void __launch_bounds__(NT)
 k_bucket_sums(const XYZZ<F>* __restrict__ buckets, int lr, int lc, XYZZ<F>* __restrict__ out) {
     extern __shared__ unsigned char smraw[];
     XYZZ<F>* s0 = reinterpret_cast<XYZZ<F>*>(smraw);
@@ -501,15 +503,15 @@ k_bucket_sums(const XYZZ<F>* __restrict__ buckets, int lr, int lc, XYZZ<F>* __re
     if (t < len) s0[t] = base[t * stride];
     else s0[t] = XYZZ<F>::identity();
 #pragma unroll 1
-    for (uint32_t i = t + kReduceThreads; i < len; i += kReduceThreads) xyzz_add_mem(&s0[t], &s0[t], &base[i * stride]);
-    block_sum_inplace<F, kReduceThreads>(s0);
+    for (uint32_t i = t + NT; i < len; i += NT) xyzz_add_mem(&s0[t], &s0[t], &base[i * stride]);
+    block_sum_inplace<F, NT>(s0);
     if (t == 0) out[g] = s0[0];
 }
 
 // stage 2: CTA j < lr: 2^(j+lc) * sum_{hi: bit j} Row[hi];  CTA lr + j, j < lc: 2^j * sum_{lo: bit j} Col[lo];
 //          CTA lr + lc: sum_hi Row[hi].  terms -> sums[2^lr + 2^lc ..]; the last CTA adds them into *out.
-template <class F>
-__global__ void __launch_bounds__(kReduceThreads)
+template <class F, int NT>
+__global__ void __launch_bounds__(NT)
 k_bucket_weighted(XYZZ<F>* __restrict__ sums, int lr, int lc, unsigned int* __restrict__ counter, XYZZ<F>* __restrict__ out) {
     extern __shared__ unsigned char smraw[];
     XYZZ<F>* s0 = reinterpret_cast<XYZZ<F>*>(smraw);
@@ -523,9 +525,9 @@ k_bucket_weighted(XYZZ<F>* __restrict__ sums, int lr, int lc, unsigned int* __re
     XYZZ<F>* terms = sums + ((size_t)1 << lr) + ((size_t)1 << lc);
     s0[t] = XYZZ<F>::identity();
 #pragma unroll 1
-    for (uint32_t i = t; i < len; i += kReduceThreads)
+    for (uint32_t i = t; i < len; i += NT)
         if (bit < 0 || ((i >> bit) & 1)) xyzz_add_mem(&s0[t], &s0[t], &src[i]);
-    block_sum_inplace<F, kReduceThreads>(s0);
+    block_sum_inplace<F, NT>(s0);
     if (t == 0) {
         const int dbl = bit < 0 ? 0 : (g < lr ? bit + lc : bit);
 #pragma unroll 1
@@ -546,7 +548,7 @@ k_bucket_weighted(XYZZ<F>* __restrict__ sums, int lr, int lc, unsigned int* __re
     } else {
         s0[t] = XYZZ<F>::identity();
     }
-    block_sum_inplace<F, kReduceThreads>(s0);
+    block_sum_inplace<F, NT>(s0);
     if (t == 0) {
         s0[0].store(out);
         *counter = 0;
@@ -719,8 +721,8 @@ int bases_build(zkr_ctx* ctx, zkr_bases* b, const char* h_points, size_t n_src, 
     b->bytes += wk.bytes;
     // per device, so once per work-buffer allocation rather than once per process (cold path, idempotent): a process
     // that drives several GPUs must opt in to > 48 KB of dynamic shared memory on each of them
-    ZKR_CUDA(cudaFuncSetAttribute(k_bucket_sums<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(XB * kReduceThreads)));
-    ZKR_CUDA(cudaFuncSetAttribute(k_bucket_weighted<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(XB * kReduceThreads)));
+    ZKR_CUDA(cudaFuncSetAttribute((k_bucket_sums<F, kReduceThreads>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(XB * kReduceThreads)));
+    ZKR_CUDA(cudaFuncSetAttribute((k_bucket_weighted<F, kReduceThreads>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(XB * kReduceThreads)));
     ZKR_CUDA(cudaFuncSetAttribute((k_accum_affine<F, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
     ZKR_CUDA(cudaFuncSetAttribute((k_accum_affine<F, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
     ZKR_CUDA(cudaFuncSetAttribute(k_bucket_gather<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(XB * kGatherThreads)));
@@ -809,9 +811,9 @@ int msm_run(zkr_ctx* ctx, cudaStream_t st, const zkr_bases* b, const uint32_t* d
     }
     // bucket reduction: row / column sums, then bit-decomposed weighted sums (see k_bucket_sums)
     const int lc = (c - 1) / 2, lr = c - 1 - lc;
-    ZKR_LAUNCH(ctx, k_bucket_sums<F>, (1u << lr) + (1u << lc), kReduceThreads, XB * kReduceThreads, st, buckets, lr, lc,
+    ZKR_LAUNCH(ctx, (k_bucket_sums<F, kReduceThreads>), (1u << lr) + (1u << lc), kReduceThreads, XB * kReduceThreads, st, buckets, lr, lc,
                (XYZZ<F>*)wk.red);
-    ZKR_LAUNCH(ctx, k_bucket_weighted<F>, lr + lc + 1, kReduceThreads, XB * kReduceThreads, st, (XYZZ<F>*)wk.red, lr, lc,
+    ZKR_LAUNCH(ctx, (k_bucket_weighted<F, kReduceThreads>), lr + lc + 1, kReduceThreads, XB * kReduceThreads, st, (XYZZ<F>*)wk.red, lr, lc,
                wk.red_counter, d_out);
     return ZKR_OK;
 }
