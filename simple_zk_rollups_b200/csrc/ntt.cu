@@ -139,6 +139,7 @@ struct PassFuse {
     const Fr* kconst;    // ST_HFINAL: K
     Fr* out;             // ST_HFINAL: destination (null = data)
     const Fr* twfull;    // full inter-pass twiddle table of this pass (null = two-level)
+    Fr* data2;           // second vector transformed by the same launch (blockIdx.y == 1); null = one vector
     int ld_op, st_op;
 };
 
@@ -148,7 +149,7 @@ struct PassFuse {
 // (profiles/r02_ntt_radix_ab.json) -- the extra shared-memory round trip per pass costs more than the extra warps hide.
 template <bool DIT, int MODE, int RL>
 __global__ void __launch_bounds__(256, RL == 3 ? 2 : 3)
-k_ntt_pass(Fr* __restrict__ data, int k, int c, int s, int ls_, int chunk_log, unsigned ctw_, const Fr* __restrict__ W,
+k_ntt_pass(Fr* data, int k, int c, int s, int ls_, int chunk_log, unsigned ctw_, const Fr* __restrict__ W,
            int kw, const Fr* __restrict__ tlo, const Fr* __restrict__ thi, int lb, int tw_shift, NttXchg xp, PassFuse fz) {
     extern __shared__ uint32_t sm[];
     constexpr bool kSlab = MODE == 1 || MODE == 3;
@@ -161,6 +162,9 @@ k_ntt_pass(Fr* __restrict__ data, int k, int c, int s, int ls_, int chunk_log, u
     const unsigned cgmask = (1u << (ls - c)) - 1;
     const unsigned cg = blockIdx.x & cgmask;
     const size_t q = blockIdx.x >> (ls - c);
+    // two independent transforms of one size can share a launch (the H pipeline's A and B): twice the CTAs per wave
+    // quantum, half the launches
+    if (MODE == 0 && blockIdx.y) data = fz.data2;
     Fr* chunk = data + (q << chunk_log);
     const unsigned cm = cg << c;             // first column of the tile in memory
     const unsigned c0 = ctw + cm;            // ... and in the transform's global coordinates
@@ -569,12 +573,13 @@ static int launch_pass(zkr_ctx* ctx, cudaStream_t st, const NttTables* t, Fr* da
     const size_t smem = (size_t)8 * (tile + (tile >> 3) + 4) * sizeof(uint32_t);
     // the pass whose write-back is the all-to-all (remote stores) is timed on its own: bench.py's exchange GB/s
     const int pid = (MODE == 1 || MODE == 2) ? PROF_NTT_XCHG : PROF_NTT_PASS;
-    const int pslot = ctx->prof_begin(pid, st, prof_units);
+    const dim3 grid(g.blocks, (MODE == 0 && fz.data2) ? 2 : 1);
+    const int pslot = ctx->prof_begin(pid, st, prof_units * grid.y);
     if (dit) {
-        ZKR_LAUNCH(ctx, (k_ntt_pass<true, MODE == 1 ? 3 : MODE, 3>), g.blocks, threads, smem, st, data, g.k, g.c, g.s,
+        ZKR_LAUNCH(ctx, (k_ntt_pass<true, MODE == 1 ? 3 : MODE, 3>), grid, threads, smem, st, data, g.k, g.c, g.s,
                    g.ls, g.chunk_log, g.ctw, W, t->kw, tlo, thi, t->lb, g.tw_shift, xp, fz);
     } else {
-        ZKR_LAUNCH(ctx, (k_ntt_pass<false, (MODE == 2 || MODE == 3) ? 0 : MODE, 3>), g.blocks, threads, smem, st, data, g.k, g.c, g.s,
+        ZKR_LAUNCH(ctx, (k_ntt_pass<false, (MODE == 2 || MODE == 3) ? 0 : MODE, 3>), grid, threads, smem, st, data, g.k, g.c, g.s,
                    g.ls, g.chunk_log, g.ctw, W, t->kw, tlo, thi, t->lb, g.tw_shift, xp, fz);
     }
     ctx->prof_end(pid, pslot, st);
@@ -610,7 +615,7 @@ static int get_twfull(zkr_ctx* ctx, cudaStream_t st, NttTables* t, int i, int ch
 // first / last (nullable): fused element-wise work of the first executed pass's load (ld_op, src, in2, tab) and of the
 // last executed pass's store (st_op, in2, tab, kconst, out).
 static int ntt_run_ex(zkr_ctx* ctx, cudaStream_t st, Fr* data, int log_n, bool dit, bool inverse, const PassFuse* first,
-                      const PassFuse* last) {
+                      const PassFuse* last, Fr* data2 = nullptr) {
     NttTables* t;
     ZKR_TRY(ntt_get_tables(ctx, log_n, &t));
     if (log_n < 3) {
@@ -640,6 +645,7 @@ static int ntt_run_ex(zkr_ctx* ctx, cudaStream_t st, Fr* data, int log_n, bool d
         g.tw_shift = log_n - g.chunk_log;
         g.blocks = 1u << (log_n - g.k - g.c);
         PassFuse fz = {};
+        fz.data2 = data2;
         if (first && step == 0) {
             fz.ld_op = first->ld_op;
             fz.src = first->src;
@@ -795,13 +801,11 @@ int h_pipeline(zkr_ctx* ctx, cudaStream_t st, Fr* A, Fr* B, Fr* S, Fr* h, int lo
         mulAB.src = A;
         mulAB.in2 = B;
         ZKR_TRY(ntt_run_ex(ctx, st, S, log_m, false, true, &mulAB, nullptr));     // S <- DIF^-1(A_T . B_T)
-        ZKR_TRY(ntt_run(ctx, st, A, log_m, false, true));
-        ZKR_TRY(ntt_run(ctx, st, B, log_m, false, true));
+        ZKR_TRY(ntt_run_ex(ctx, st, A, log_m, false, true, nullptr, nullptr, B));  // A and B share every launch
         PassFuse coset = {};
         coset.ld_op = LD_TAB;
         coset.tab = t->cs_br;
-        ZKR_TRY(ntt_run_ex(ctx, st, A, log_m, true, false, &coset, nullptr));     // A, B on the coset g<omega>
-        ZKR_TRY(ntt_run_ex(ctx, st, B, log_m, true, false, &coset, nullptr));
+        ZKR_TRY(ntt_run_ex(ctx, st, A, log_m, true, false, &coset, nullptr, B));  // A, B on the coset g<omega>
         PassFuse mulP = {}, fin = {};
         mulP.ld_op = LD_MUL2;
         mulP.in2 = B;
