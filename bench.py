@@ -649,20 +649,21 @@ def sharded_blocks(env, args, key_rank0):
     part = gp.load_key_sharded(pk_bin, rank, world)
     want = bcast_bytes(proof0, 256)
     single_ms = env["max_over_ranks"](single_ms if rank == 0 else 0.0)
-    wit = np.frombuffer(wbytes, dtype=np.uint8)
+    # pinned, like the witness buffer of the one-GPU call it is compared with
+    wit_pin = torch.frombuffer(bytearray(wbytes), dtype=torch.uint8).pin_memory()
     rb = np.frombuffer(int(RS[0]).to_bytes(32, "little"), dtype=np.uint8)
     sb = np.frombuffer(int(RS[1]).to_bytes(32, "little"), dtype=np.uint8)
     got = np.zeros(256, dtype=np.uint8)
     st = _Stats()
 
     def prove_sharded():
-        _lib_check(L.zkr_prove_sharded(comm.h, part, _buf_ptr(wit), wit.size // 32, _buf_ptr(rb), _buf_ptr(sb),
+        _lib_check(L.zkr_prove_sharded(comm.h, part, C.c_void_p(wit_pin.data_ptr()), wit_pin.numel() // 32, _buf_ptr(rb), _buf_ptr(sb),
                                        _buf_ptr(got), C.byref(st)))
     t_sh = best_of(env, prove_sharded, reps)
     same = env["all_true"](got.tobytes() == want)
     info = gp.key_info(part)
     res["proof"] = {
-        "shape": args.shape, "api": "zkr_pkey_load_bin_sharded + zkr_prove_sharded (host witness, H2D + D2H inside)",
+        "shape": args.shape, "api": "zkr_pkey_load_bin_sharded + zkr_prove_sharded (pinned host witness, H2D + D2H inside)",
         "ms": round(t_sh, 3), "single_gpu_ms": round(single_ms, 3), "speedup_vs_1gpu": round(single_ms / t_sh, 3),
         "identical": bool(same), "check": "256 proof bytes on every rank == rank 0's zkr_prove on one GPU (same key, witness, r, s)",
         "exchange_bytes_per_rank": 1024 * (world - 1), "key_gb_per_rank": round(info["device_bytes"] / 1e9, 2),

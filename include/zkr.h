@@ -282,12 +282,21 @@ void zkr_comm_destroy(zkr_comm* c);
 int zkr_msm_sharded(zkr_comm* c, const zkr_bases* b, const void* scalars, size_t n_local,
                     int scalars_on_device, void* out_affine);
 
-/* One proof over `world` GPUs (latency split).  zkr_pkey_load_bin_sharded keeps only rank's contiguous point
- * range of each of the five base sets (A, B1, B2, C, hExps; blinding bases included) resident; every rank
- * receives the full witness, computes A_T/B_T and h (replicated: at rollup sizes the H pipeline is a few ms
- * and its exchange would cost more than it saves), runs its share of the five MSMs, stores the five partial
- * sums into every peer's gather slot and assembles the proof.  All ranks return the same 256 bytes, identical
- * to zkr_prove on one GPU.  Same arguments and error behaviour as zkr_prove. */
+/* One proof over `world` GPUs (latency split; SURVEY.md 8(e): "GPU0: sparse_lc + H + MSM_H; others: MSM_A, MSM_B1,
+ * MSM_B2, MSM_C; combine 5 points" -- websnark fans the same calls out to web workers inside groth16GenProof,
+ * operator/src/snarks/common.ts:29).  Every rank receives the full witness.  The first g_h ranks (the H group:
+ * 1 of 2, 2 of 4, 4 of 8) compute A_T/B_T and h and run 1/g_h of the hExps MSM each (the H pipeline does not shard at
+ * rollup sizes, so it is kept off the other ranks instead of being replicated on all of them); the four witness
+ * MSMs (A, B1, B2, C; blinding bases included) are split by contiguous point range with weights that give every
+ * rank the same modelled work (csrc/prover.cu shard_plan).  zkr_pkey_load_bin_sharded keeps only this rank's
+ * ranges resident.  Each rank blinds its own partial A / B1 (scalar multiplication is linear), stores its seven
+ * partial sums into every peer's gather slot, adds the `world` partials and assembles the proof.  All ranks return
+ * the same 256 bytes, identical to zkr_prove on one GPU.  Same arguments and error behaviour as zkr_prove, except that
+ * r32 / s32 are required (all ranks must use the same pair).
+ * zkr_shard_ranges reports the split (no GPU needed): out6 = {ab_lo, ab_hi, c_lo, c_hi, h_lo, h_hi}, ranges of rank
+ * over the n_vars + 2 points of A'/B1'/B2', the n_vars - n_public - 1 + 1 points of C', and the domain_size
+ * coefficients of h (bit-reversed order; empty outside the H group). */
+int zkr_shard_ranges(int world, int rank, uint64_t n_vars, uint64_t n_public, uint64_t domain_size, uint64_t* out6);
 int zkr_pkey_load_bin_sharded(zkr_ctx* ctx, const void* buf, size_t len, int rank, int world, zkr_pkey** out);
 int zkr_prove_sharded(zkr_comm* c, const zkr_pkey* pk, const void* witness, size_t n_signals,
                       const void* r32, const void* s32, void* out_proof, zkr_stats* stats);

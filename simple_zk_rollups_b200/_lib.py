@@ -95,6 +95,7 @@ _SIGS = {
     "zkr_comm_destroy": (None, [C.c_void_p]),
     "zkr_msm_sharded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "zkr_pkey_load_bin_sharded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "zkr_shard_ranges": (C.c_int, [C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]),
     "zkr_prove_sharded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.POINTER(Stats)]),
     "zkr_ntt_sharded_rows_log": (C.c_int, [C.c_int, C.c_int]),

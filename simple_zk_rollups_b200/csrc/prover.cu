@@ -13,6 +13,7 @@
 // The blinding terms ride inside the MSMs as extra bases, so the only scalar multiplications left
 // are s*pi_a and r*pib1 (two threads, overlapped with the G2 / C / H MSMs on other streams).
 #include <sys/random.h>
+#include <unistd.h>
 
 #include <cstdlib>
 #include <cstring>
@@ -31,6 +32,7 @@ struct zkr_pkey {
     int log_m = 0;
     int rank = 0, world = 1;       // world > 1: the five base sets hold this rank's point range only
     uint64_t h_lo = 0;             // first h coefficient (bit-reversed order) of this rank's hExps slice
+    uint64_t h_count = 0;          // size of that slice; 0 = this rank is outside the H group (shard_plan) and skips the H chain
     // polsA / polsB as CSR by constraint row (coefficients Fr-M exactly as in the key)
     uint32_t *a_ptr = nullptr, *a_sig = nullptr, *b_ptr = nullptr, *b_sig = nullptr;
     Fr *a_coef = nullptr, *b_coef = nullptr;
@@ -47,7 +49,7 @@ struct zkr_pkey {
     // zkr_prove_batch: second witness buffer + upload events, so that witness i+1 is uploaded while proof i runs
     Fr* wext2 = nullptr;
     cudaEvent_t ev_up[2] = {};
-    cudaEvent_t ev[16] = {};
+    cudaEvent_t ev[19] = {};   // 0..15 stage timing (zkr_stats), 16..18 sharded tail (ZKR_TIMELINE)
     // B1' and B2' take the same scalars through the same compaction map and window plan (B1_i is the point at infinity
     // exactly when B2_i is): one digit extraction + radix sort, done on pi_b's stream, serves both MSMs
     bool share_b_sort = false;
@@ -177,11 +179,12 @@ __global__ void k_finish(const char* res, char* proof, int fermat) {
     }
 }
 
-// sharded prove: res[e] = sum over ranks of the gathered partial results (block e: A, B1, C, H in G1; B2 in G2)
+// sharded prove: res[e] = sum over ranks of the gathered partial results (block e: B2 in G2; A, B1, C, H and, when
+// every rank blinded its own partials, T1, T2 in G1)
 __global__ void k_sum_res(const char* slots, int world, char* res) {
-    const int offs[5] = {R_A, R_B1, R_C, R_H, R_B2};
+    const int offs[7] = {R_B2, R_A, R_B1, R_C, R_H, R_T1, R_T2};
     const int off = offs[blockIdx.x];
-    if (blockIdx.x < 4) {
+    if (blockIdx.x > 0) {
         G1XYZZ acc = G1XYZZ::load(slots + off);
 #pragma unroll 1
         for (int r = 1; r < world; r++) acc.add(G1XYZZ::load(slots + (size_t)r * kCommSlotBytes + off));
@@ -279,6 +282,53 @@ static void shard_range(uint64_t total, int rank, int world, uint64_t* lo, uint6
     *hi = *lo + base + ((uint64_t)rank < rem ? 1 : 0);
 }
 
+// How one proof is split over `world` ranks (SURVEY.md 8(e) "single-proof latency split": one part of the box runs
+// sparse LC + H pipeline + the hExps MSM, the rest runs the witness MSMs; websnark fans the same calls out to web
+// workers, operator/src/snarks/common.ts:29).  The H pipeline does not shard at rollup sizes, so replicating it on every
+// rank costs 1.7 ms per rank.  Instead only the first g_h ranks (the "H group") run it, each followed by 1/g_h of the
+// hExps MSM; the witness MSMs (A', B1', B2', C') are split by point range with WEIGHTS: a fraction x of the points
+// to each H-group rank, y to each of the others, chosen so that every rank gets the same modelled work
+//     H-group rank:  P + MH / g_h + x W        other rank:  y W         g_h x + (world - g_h) y = 1
+// in units of one G1 point of a 2^20 MSM (P = H pipeline, MH = m, W = n (2 + 2.4) + nc; a G2 point costs 2.4 G1
+// points, the H pipeline 0.85 m: profiles/r02_launch_shares.md).  ZKR_SHARD_TASKS=0 restores the uniform split with
+// the H pipeline on every rank; ZKR_SHARD_GH / ZKR_SHARD_X override g_h / x (tools/gpu_jobs/r02_sharded_tasks.sh).
+// Every rank of a job must see the same values.
+struct ShardPlan {
+    int g_h = 1;
+    double x = 1, y = 1;
+    bool uniform = true;
+};
+static ShardPlan shard_plan(int world, uint64_t n, uint64_t nc, uint64_t m) {
+    ShardPlan p;
+    p.g_h = world;
+    p.x = p.y = 1.0 / world;
+    const char* e = getenv("ZKR_SHARD_TASKS");
+    if (world == 1 || (e && atoi(e) == 0)) return p;
+    p.uniform = false;
+    p.g_h = world <= 2 ? 1 : world / 2;
+    if ((e = getenv("ZKR_SHARD_GH")) && atoi(e) >= 1 && atoi(e) < world) p.g_h = atoi(e);
+    const double P = 0.85 * (double)m, MH = (double)m, W = (double)n * 4.4 + (double)nc;
+    const double T = (p.g_h * P + MH + W) / world;
+    p.x = (T - P - MH / p.g_h) / W;
+    if ((e = getenv("ZKR_SHARD_X"))) p.x = atof(e);
+    if (p.x < 0.06) p.x = 0;                       // not worth four more latency chains beside the H chain
+    if (p.x * p.g_h > 1) p.x = 1.0 / p.g_h;
+    p.y = (1.0 - p.g_h * p.x) / (world - p.g_h);
+    return p;
+}
+// rank's [lo, hi) of the witness MSMs' `total` points under the plan (cumulative weights, last rank ends at total)
+static void plan_range(const ShardPlan& p, uint64_t total, int rank, int world, uint64_t* lo, uint64_t* hi) {
+    if (p.uniform) return shard_range(total, rank, world, lo, hi);
+    auto cum = [&](int r) -> uint64_t {
+        if (r >= world) return total;
+        const double f = r <= p.g_h ? r * p.x : p.g_h * p.x + (r - p.g_h) * p.y;
+        const uint64_t v = (uint64_t)(f * (double)total);
+        return v > total ? total : v;
+    };
+    *lo = cum(rank);
+    *hi = cum(rank + 1);
+}
+
 static int pkey_load(zkr_ctx* ctx, const void* vbuf, size_t len, int rank, int world, zkr_pkey** out) {
     if (!ctx || !vbuf || !out || world < 1 || rank < 0 || rank >= world) return ZKR_E_INVALID;
     *out = nullptr;
@@ -310,6 +360,7 @@ static int pkey_load(zkr_ctx* ctx, const void* vbuf, size_t len, int rank, int w
     pk->world = world;
     while ((1u << pk->log_m) < v.m) pk->log_m++;
     uint64_t lo = 0, hi = 0;
+    const ShardPlan plan = shard_plan(world, n, n - l - 1, m);
     int rc = ZKR_OK;
 #define PK_TRY(expr)              \
     do {                          \
@@ -354,7 +405,7 @@ static int pkey_load(zkr_ctx* ctx, const void* vbuf, size_t len, int rank, int w
         for (uint32_t i = 0; i < N + 2; i++) sidx[i] = i;            // n -> 1, n+1 -> r
         pk->A = bases_alloc();
         bases_set_group(pk->A, 1);
-        shard_range(n + 2, rank, world, &lo, &hi);
+        plan_range(plan, n + 2, rank, world, &lo, &hi);
         PK_TRY(bases_build_g1(ctx, pk->A, pts.data() + 64 * lo, hi - lo, 0, st, sidx.data() + lo));
         // B1' = [B1.., beta1, delta1] x [w.., 1, s]
         memcpy(pts.data(), buf + v.pPB1, 64 * n);
@@ -382,7 +433,7 @@ static int pkey_load(zkr_ctx* ctx, const void* vbuf, size_t len, int rank, int w
         sidx[nc] = N + 3;
         pk->C = bases_alloc();
         bases_set_group(pk->C, 1);
-        shard_range(nc + 1, rank, world, &lo, &hi);
+        plan_range(plan, nc + 1, rank, world, &lo, &hi);
         PK_TRY(bases_build_g1(ctx, pk->C, pts.data() + 64 * lo, hi - lo, 0, st, sidx.data() + lo));
     }
     {   // H: hExps permuted to bit-reversed order (the H pipeline leaves h bit-reversed)
@@ -395,8 +446,10 @@ static int pkey_load(zkr_ctx* ctx, const void* vbuf, size_t len, int rank, int w
         }
         pk->H = bases_alloc();
         bases_set_group(pk->H, 1);
-        shard_range(m, rank, world, &lo, &hi);
+        if (rank < plan.g_h) shard_range(m, rank, plan.g_h, &lo, &hi);
+        else lo = hi = 0;                                             // not in the H group: no H pipeline, no hExps slice
         pk->h_lo = lo;
+        pk->h_count = hi - lo;
         PK_TRY(bases_build_g1(ctx, pk->H, pts.data() + 64 * lo, hi - lo, 0, st, nullptr));
     }
     // work buffers
@@ -444,6 +497,18 @@ extern "C" int zkr_pkey_load_bin(zkr_ctx* ctx, const void* vbuf, size_t len, zkr
     return pkey_load(ctx, vbuf, len, 0, 1, out);
 }
 
+extern "C" int zkr_shard_ranges(int world, int rank, uint64_t n_vars, uint64_t n_public, uint64_t domain_size,
+                                uint64_t* out6) {
+    if (!out6 || world < 1 || rank < 0 || rank >= world || n_vars < n_public + 1) return ZKR_E_INVALID;
+    const uint64_t nc = n_vars - n_public - 1;
+    const ShardPlan plan = shard_plan(world, n_vars, nc, domain_size);
+    plan_range(plan, n_vars + 2, rank, world, &out6[0], &out6[1]);
+    plan_range(plan, nc + 1, rank, world, &out6[2], &out6[3]);
+    if (rank < plan.g_h) shard_range(domain_size, rank, plan.g_h, &out6[4], &out6[5]);
+    else out6[4] = out6[5] = 0;
+    return ZKR_OK;
+}
+
 extern "C" int zkr_pkey_load_bin_sharded(zkr_ctx* ctx, const void* vbuf, size_t len, int rank, int world, zkr_pkey** out) {
     return pkey_load(ctx, vbuf, len, rank, world, out);
 }
@@ -485,8 +550,14 @@ static int prove_enqueue(zkr_ctx* ctx, const zkr_pkey* pk, char* d_proof, bool t
     const uint32_t* w = (const uint32_t*)wext;
     // experiment knob (tools/prio_sweep.py): ZKR_H_FIRST=1 runs sparse LC + the NTT pipeline before any MSM starts
     const bool h_first = getenv("ZKR_H_FIRST") && atoi(getenv("ZKR_H_FIRST")) != 0;
+    const bool has_h = pk->h_count != 0;   // false: a rank outside the H group of a sharded proof (shard_plan)
     auto h_front = [&]() -> int {
         if (timed) cudaEventRecord(ev[0], sH);
+        if (!has_h) {
+            if (timed) cudaEventRecord(ev[1], sH);
+            if (timed) cudaEventRecord(ev[2], sH);
+            return ZKR_OK;
+        }
         ZKR_LAUNCH(ctx, k_sparse_lc, dim3(ceil_div(m, 128), 2), 128, 0, sH, pk->a_ptr, pk->a_sig, pk->a_coef, pk->b_ptr,
                    pk->b_sig, pk->b_coef, wext, pk->at, pk->bt, m);
         if (timed) cudaEventRecord(ev[1], sH);
@@ -522,7 +593,11 @@ static int prove_enqueue(zkr_ctx* ctx, const zkr_pkey* pk, char* d_proof, bool t
         ZKR_CUDA(cudaStreamWaitEvent(sHm, ctx->ev_join[6], 0));
     }
     ZKR_TRY(delayed('H', sHm));
-    ZKR_TRY(msm_run_g1(ctx, sHm, pk->H, (const uint32_t*)(pk->h + pk->h_lo), pk->res + R_H, nullptr, nullptr, nullptr, late('h')));
+    if (has_h) {
+        ZKR_TRY(msm_run_g1(ctx, sHm, pk->H, (const uint32_t*)(pk->h + pk->h_lo), pk->res + R_H, nullptr, nullptr, nullptr, late('h')));
+    } else {
+        ZKR_CUDA(cudaMemsetAsync(pk->res + R_H, 0, 128, sHm));   // the identity (ZZ = 0)
+    }
     if (timed) cudaEventRecord(ev[3], sHm);
     // A, then s * pi_a
     if (timed) cudaEventRecord(ev[4], sA);
@@ -542,21 +617,32 @@ static int prove_enqueue(zkr_ctx* ctx, const zkr_pkey* pk, char* d_proof, bool t
     ZKR_TRY(delayed('C', sC));
     ZKR_TRY(msm_run_g1(ctx, sC, pk->C, w, pk->res + R_C, nullptr, nullptr, nullptr, late('c')));
     if (timed) cudaEventRecord(ev[11], sC);
-    if (comm && comm->world > 1) {
-        // sharded: the five results are partial sums over this rank's point ranges.  Store them into every
-        // peer's gather slot, add the `world` partials, then blind (s*pi_a, r*pib1 need the full A, B1).
-        if (par) ZKR_TRY(ctx->join(n_fork));
-        int parity = 0;
-        ZKR_TRY(comm_allgather_small(comm, us, pk->res, R_TOTAL, &parity));
-        ZKR_LAUNCH(ctx, k_sum_res, 5, 1, 0, us, comm_gather_slot(comm, comm->rank, parity, 0), comm->world, pk->res);
-        ZKR_LAUNCH(ctx, k_blind_muls, 2, 32 * kBlindWarps, kBlindSmem, us, pk->res, wext, n);
-    } else {
-        // the two blinding scalar multiplications need A and B1
+    // the two blinding scalar multiplications T1 = s * pi_a, T2 = r * pib1 need A and B1
+    auto blind = [&]() -> int {
         if (par) {
             ZKR_CUDA(cudaEventRecord(ctx->ev_join[2], sB1));
             ZKR_CUDA(cudaStreamWaitEvent(sA, ctx->ev_join[2], 0));
         }
         ZKR_LAUNCH(ctx, k_blind_muls, 2, 32 * kBlindWarps, kBlindSmem, sA, pk->res, wext, n);
+        return ZKR_OK;
+    };
+    if (comm && comm->world > 1) {
+        // sharded: the results are partial sums over this rank's point ranges.  Scalar multiplication is linear, so each
+        // rank blinds its own partial A / B1 behind the A chain (off the critical H chain) and the gather sums seven
+        // partials; ZKR_SHARDED_BLIND_LATE=1 (A/B knob) blinds the summed A / B1 after the gather instead.
+        static const bool blind_late = getenv("ZKR_SHARDED_BLIND_LATE") && atoi(getenv("ZKR_SHARDED_BLIND_LATE")) != 0;
+        if (!blind_late) ZKR_TRY(blind());
+        if (par) ZKR_TRY(ctx->join(n_fork));
+        if (timed) cudaEventRecord(ev[16], us);
+        int parity = 0;
+        ZKR_TRY(comm_allgather_small(comm, us, pk->res, R_TOTAL, &parity));
+        if (timed) cudaEventRecord(ev[17], us);
+        ZKR_LAUNCH(ctx, k_sum_res, blind_late ? 5 : 7, 1, 0, us, comm_gather_slot(comm, comm->rank, parity, 0), comm->world,
+                   pk->res);
+        if (timed) cudaEventRecord(ev[18], us);
+        if (blind_late) ZKR_LAUNCH(ctx, k_blind_muls, 2, 32 * kBlindWarps, kBlindSmem, us, pk->res, wext, n);
+    } else {
+        ZKR_TRY(blind());
         if (par) ZKR_TRY(ctx->join(n_fork));
     }
     if (timed) cudaEventRecord(ev[12], us);
@@ -680,6 +766,21 @@ static int prove_host(zkr_ctx* ctx, const zkr_pkey* pk, const void* witness, siz
     s.msm_c_ms = el(10, 11);
     s.assemble_ms = el(12, 13);
     s.kernel_launches = ctx->launches - launches0;
+    // ZKR_TIMELINE=1 (measurement knob): offsets of every stage event from the start of the call, on stderr --
+    // the zkr_stats durations do not say when a chain started (tools/gpu_jobs/r02_sharded_timeline.sh)
+    static const bool timeline = getenv("ZKR_TIMELINE") && atoi(getenv("ZKR_TIMELINE")) != 0;
+    if (timeline) {
+        static const char* names[14] = {"lc0", "lc1", "ntt1", "msm_h1", "a0", "a1", "b2_0", "b2_1", "b1_0", "b1_1",
+                                        "c0", "c1", "tail0", "finish1"};
+        char line[640];
+        int o = snprintf(line, sizeof line, "zkr timeline rank %d/%d total %.3f:", pk->rank, pk->world, s.total_ms);
+        for (int i = 0; i < 14; i++) o += snprintf(line + o, sizeof line - o, " %s=%.3f", names[i], el(14, i));
+        if (comm && comm->world > 1)
+            o += snprintf(line + o, sizeof line - o, " joined=%.3f gathered=%.3f summed=%.3f", el(14, 16), el(14, 17), el(14, 18));
+        line[o++] = '\n';
+        if (write(2, line, (size_t)o) < 0) {   // one write per line: the ranks of a torchrun job share the pipe
+        }
+    }
     ctx->last_stats = s;
     if (stats) *stats = s;
     return ZKR_OK;
