@@ -668,8 +668,11 @@ def sharded_blocks(env, args, key_rank0):
         "identical": bool(same), "check": "256 proof bytes on every rank == rank 0's zkr_prove on one GPU (same key, witness, r, s)",
         "exchange_bytes_per_rank": 1024 * (world - 1), "key_gb_per_rank": round(info["device_bytes"] / 1e9, 2),
         "stage_ms": {k: round(v, 3) for k, v in st.as_dict().items() if k.endswith("_ms")},
-        "limited_by": "H pipeline replicated on every rank + per-MSM latency chains (sort, boundary levels, bucket reduction) "
-                      "that do not shrink with the point range (DESIGN.md 6)"}
+        "split": "task-aware (DESIGN.md 6): sparse LC + H pipeline + hExps MSM on the first max(1, N/2) ranks only, the witness MSMs' "
+                 "point ranges weighted so that every rank carries the same modelled work; ZKR_SHARD_TASKS=0 = uniform ranges, H on every rank",
+        "limited_by": "the 0.55 ms witness upload every rank repeats, the H chain (LC + 6 transforms + MSM, about 5 ms at 2^20) that bounds "
+                      "its group however few witness points it also takes, and per-MSM latency chains (sort passes, gather, bucket "
+                      "reduction, blinding: about 1.5 ms) that do not shrink with the point range (DESIGN.md 6)"}
     log("[bench] sharded proof: %.2f ms on %d GPUs vs %.2f ms on one, identical=%s (%.1f s)" % (
         t_sh, world, single_ms, same, time.time() - t0))
     gp.L.zkr_pkey_free(part)
