@@ -424,7 +424,12 @@ def run_ours(args):
                         "peak_source": "plain IMAD chain measured in this run (zkr_microbench); MEASURED_PEAKS.json has no integer peak",
                         "practical_peak_frac": round((g1_madds * MADD_MODMULS / (g1_ms * 1e-3)) / modmul_peak.value, 4),
                         "practical_peak_note": "vs the register-resident Fq modmul chain measured in this run (%.1f G modmul/s): "
-                                               "IMAD.WIDE issues at half the IMAD rate" % (modmul_peak.value / 1e9),
+                                               "IMAD.WIDE issues at half the IMAD rate.  The count is the ALGORITHMIC 10 modmul per "
+                                               "mixed addition (SURVEY.md 8(d)); since round 2 the kernel executes 1288 IMAD per "
+                                               "addition instead of 1360 (y3 = r (q - x3) - y ppp as one two-product pass with one "
+                                               "reduction), which is how this fraction can exceed the chain's" % (modmul_peak.value / 1e9),
+                        "executed_imad_per_madd": 8 * MODMUL_IMAD + 200,
+                        "executed_frac_of_plain_imad_peak": round(g1_madds * (8 * MODMUL_IMAD + 200) / (g1_ms * 1e-3) / imad_peak.value, 4),
                         "launches": g1_cnt, "avg_launch_ms": round(g1_ms / g1_cnt, 4),
                         "algorithmic_units_per_launch": "%.0f mixed adds x 10 modmul x 136 IMAD" % (g1_madds / g1_cnt),
                         "share_of_serial_step": round(g1_ms / prof_steps / serial_ms, 4),

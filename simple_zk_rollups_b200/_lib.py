@@ -4,7 +4,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libzkr.so")
+# ZKR_LIB: load a variant build instead (simple_zk_rollups_b200/build.py, A/B of compile-time choices on one GPU box)
+LIB_PATH = os.environ.get("ZKR_LIB") or os.path.join(HERE, "libzkr.so")
 
 PROOF_BYTES = 256
 

@@ -12,15 +12,18 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(CSRC, "build")
-LIB = os.path.join(HERE, "libzkr.so")
+# A/B of compile-time variants on one GPU box: ZKR_BUILD_VARIANT=name ZKR_BUILD_DEFINES="-DX=1 ..." builds libzkr_<name>.so
+# beside the product library (own object directory); ZKR_LIB=<path> makes _lib.py load it.  Never part of build().
+_VARIANT = os.environ.get("ZKR_BUILD_VARIANT", "")
+OBJ = os.path.join(CSRC, "build" + ("_" + _VARIANT if _VARIANT else ""))
+LIB = os.path.join(HERE, "libzkr%s.so" % ("_" + _VARIANT if _VARIANT else ""))
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17", "--expt-relaxed-constexpr",
     "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function",
     "-Xptxas", "-v" if os.environ.get("ZKR_PTXAS_V") else "-O3",
-]
+] + (os.environ.get("ZKR_BUILD_DEFINES", "").split() if _VARIANT else [])
 
 
 def _nvcc():

@@ -9,6 +9,15 @@
 #pragma once
 #include "fp.cuh"
 
+#if !defined(__CUDACC__) && !defined(__noinline__)
+#define __noinline__
+#endif
+#ifndef ZKR_LAZY_TAIL
+// 1 (default): the full XYZZ addition and the doublings (bucket gather / reduction, blinding, tails) use the lazily reduced
+// forms as well; 0 keeps the round-1 arithmetic there (A/B: profiles/r02_lazy_reduction_ab.json, build.py ZKR_BUILD_VARIANT)
+#define ZKR_LAZY_TAIL 1
+#endif
+
 namespace zkr {
 
 template <class F>
@@ -63,7 +72,11 @@ struct XYZZ {
         F xx = p.x.sqr();
         F m = xx.dbl() + xx;
         F x3 = m.sqr() - s.dbl();
+#if ZKR_LAZY_TAIL
+        F y3 = F::msub(m, s - x3, w, p.y);
+#else
         F y3 = m * (s - x3) - w * p.y;
+#endif
         return {x3, y3, v, w};
     }
 
@@ -76,8 +89,13 @@ struct XYZZ {
         F xx = x.sqr();
         F m = xx.dbl() + xx;
         F x3 = m.sqr() - s.dbl();
+#if ZKR_LAZY_TAIL
+        F y3 = F::msub(m, s - x3, w, y);
+        return {x3, y3, F::mul_l(v, zz), F::mul_l(w, zzz)};
+#else
         F y3 = m * (s - x3) - w * y;
         return {x3, y3, v * zz, w * zzz};
+#endif
     }
 
     // this += affine q  (q must not be infinity)
@@ -103,12 +121,43 @@ struct XYZZ {
         zzz = zzz * ppp;
     }
 
+    // Same addition with the sums of products reduced once (fp.cuh "sums of products"): y3 = r (q - x3) - y ppp is one
+    // two-product pass for G1 (200 instead of 272 multiplier instructions, one subtraction and one final correction
+    // fewer) and two four-product passes for G2; G2's six plain products use the schoolbook-lazy Fq2::mul_l.
+    // Results are canonical and bit-identical to madd().
+    __device__ __forceinline__ void madd_lazy(const Affine<F>& q) {
+        if (is_inf()) {
+            x = q.x; y = q.y; zz = F::one(); zzz = F::one();
+            return;
+        }
+        F p = F::mul_l(q.x, zz) - x;
+        F r = F::mul_l(q.y, zzz) - y;
+        if (p.is_zero()) {
+            if (r.is_zero()) *this = dbl_affine(q);
+            else *this = identity();
+            return;
+        }
+        F pp = p.sqr();
+        F ppp = F::mul_l(p, pp);
+        F qq = F::mul_l(x, pp);
+        F x3 = r.sqr() - ppp - qq.dbl();
+        y = F::msub(r, qq - x3, y, ppp);
+        x = x3;
+        zz = F::mul_l(zz, pp);
+        zzz = F::mul_l(zzz, ppp);
+    }
+
     // this += o
     __device__ __forceinline__ void add(const XYZZ& o) {
         if (o.is_inf()) return;
         if (is_inf()) { *this = o; return; }
+#if ZKR_LAZY_TAIL
+        F u1 = F::mul_l(x, o.zz), u2 = F::mul_l(o.x, zz);
+        F s1 = F::mul_l(y, o.zzz), s2 = F::mul_l(o.y, zzz);
+#else
         F u1 = x * o.zz, u2 = o.x * zz;
         F s1 = y * o.zzz, s2 = o.y * zzz;
+#endif
         F p = u2 - u1;
         F r = s2 - s1;
         if (p.is_zero()) {
@@ -117,6 +166,15 @@ struct XYZZ {
             return;
         }
         F pp = p.sqr();
+#if ZKR_LAZY_TAIL          // sums of products reduced once, Fq2 products schoolbook-lazy (see madd_lazy); same words out
+        F ppp = F::mul_l(p, pp);
+        F qq = F::mul_l(u1, pp);
+        F x3 = r.sqr() - ppp - qq.dbl();
+        y = F::msub(r, qq - x3, s1, ppp);
+        x = x3;
+        zz = F::mul_l(F::mul_l(zz, o.zz), pp);
+        zzz = F::mul_l(F::mul_l(zzz, o.zzz), ppp);
+#else
         F ppp = p * pp;
         F qq = u1 * pp;
         F x3 = r.sqr() - ppp - qq.dbl();
@@ -124,6 +182,7 @@ struct XYZZ {
         x = x3;
         zz = zz * o.zz * pp;
         zzz = zzz * o.zzz * ppp;
+#endif
     }
 
     // affine, Montgomery form; identity -> (0, 0)

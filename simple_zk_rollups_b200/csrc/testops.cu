@@ -23,7 +23,13 @@ __global__ void k_field_op(int op, const uint32_t* a, const uint32_t* b, uint32_
         case 3: r = x.sqr(); break;
         case 4: r = x.inverse(); break;
         case 5: r = x.to_mont(); break;
-        default: r = x.from_mont(); break;
+        case 6: r = x.from_mont(); break;
+        case 7: r = F::mul2(x, y, x + y, x - y); break;      // x y + (x + y)(x - y), one reduction (fp.cuh mont_mul2_raw)
+        case 8: r = F::msub(x, y, x + y, x - y); break;      // x y - (x + y)(x - y)
+        default: {                                           // 9: four products x y + (x+y)(x-y) + x (x-y) + (x+y) y
+            F s = x + y, d = x - y;
+            mont_mul4_raw<typename F::Params>(r.v, x.v, y.v, s.v, d.v, x.v, d.v, s.v, y.v);
+        }
     }
     r.store(out + 8 * i);
 }
@@ -42,12 +48,19 @@ __global__ void k_curve_op(int op, const char* p, const char* q, char* out, size
         acc = acc.dbl();
     } else if (op == 2) {
         acc = scalar_mul(acc, Fr::load(q + 32 * i));
-    } else {
+    } else if (op == 3) {
         Affine<F> Q = Affine<F>::load(q + AB * i);
         XYZZ<F> d = acc.dbl();
         XYZZ<F> qq = XYZZ<F>::from_affine(Q).dbl();            // non-trivial zz on both operands
         d.add(qq);                                             // 2P + 2Q
         acc = d;
+    } else {                                                   // 4 / 5: 2P + Q through madd / madd_lazy (non-trivial zz)
+        Affine<F> Q = Affine<F>::load(q + AB * i);
+        acc = acc.dbl();
+        if (!Q.is_inf()) {
+            if (op == 4) acc.madd(Q);
+            else acc.madd_lazy(Q);
+        }
     }
     acc.to_affine().store(out + AB * i);
 }
@@ -109,6 +122,20 @@ __global__ void k_bench_madd(uint32_t* out, int iters) {
     G1XYZZ acc = G1XYZZ::dbl_affine(g);
     for (int it = 0; it < iters; it++) acc.madd(g);
     if (acc.x.v[0] == 0x12345678u && acc.zz.v[7] == 1) out[0] = acc.y.v[3];
+}
+
+// 12 / 13 / 14: register-resident chains of the lazily reduced G1 addition and of the G2 addition in both forms
+template <class F, bool LAZY>
+__global__ void k_bench_madd_v(uint32_t* out, int iters) {
+    Affine<F> g;
+    g.x = F::one();
+    g.y = F::one().dbl();
+    XYZZ<F> acc = XYZZ<F>::dbl_affine(g);
+    for (int it = 0; it < iters; it++) {
+        if (LAZY) acc.madd_lazy(g);
+        else acc.madd(g);
+    }
+    if (acc.is_inf()) acc.store(out + 64);   // never true for this chain; keeps the additions live
 }
 
 // ---- what would batched-affine bucket accumulation cost?  (measure, do not cost on paper)
@@ -263,8 +290,8 @@ __global__ void k_bench_iadd64(uint32_t* out, int iters, unsigned long long a) {
 }  // namespace
 
 extern "C" int zkr_test_field_op(zkr_ctx* ctx, int field, int op, const void* a, const void* b, void* out, size_t n) {
-    if (!ctx || !a || !out || n == 0 || op < 0 || op > 6 || (field != 0 && field != 1)) return ZKR_E_INVALID;
-    if (op <= 2 && !b) return ZKR_E_INVALID;
+    if (!ctx || !a || !out || n == 0 || op < 0 || op > 9 || (field != 0 && field != 1)) return ZKR_E_INVALID;
+    if ((op <= 2 || op >= 7) && !b) return ZKR_E_INVALID;
     DeviceGuard g(ctx->device);
     uint32_t *da = nullptr, *db = nullptr, *dout = nullptr;
     ZKR_CUDA(cudaMalloc(&da, n * 32));
@@ -286,7 +313,7 @@ extern "C" int zkr_test_field_op(zkr_ctx* ctx, int field, int op, const void* a,
 }
 
 extern "C" int zkr_test_curve_op(zkr_ctx* ctx, int group, int op, const void* p, const void* q, void* out, size_t n) {
-    if (!ctx || !p || !out || n == 0 || op < 0 || op > 3 || (group != 1 && group != 2)) return ZKR_E_INVALID;
+    if (!ctx || !p || !out || n == 0 || op < 0 || op > 5 || (group != 1 && group != 2)) return ZKR_E_INVALID;
     if (op != 1 && !q) return ZKR_E_INVALID;
     DeviceGuard g(ctx->device);
     size_t ab = group == 1 ? 64 : 128;
@@ -311,10 +338,10 @@ extern "C" int zkr_test_curve_op(zkr_ctx* ctx, int group, int op, const void* p,
 }
 
 extern "C" int zkr_microbench(zkr_ctx* ctx, int which, int iters, double* ops_per_s, float* ms_out) {
-    if (!ctx || which < 0 || which > 11 || iters <= 0 || !ops_per_s) return ZKR_E_INVALID;
+    if (!ctx || which < 0 || which > 14 || iters <= 0 || !ops_per_s) return ZKR_E_INVALID;
     DeviceGuard g(ctx->device);
     uint32_t* dout = nullptr;
-    ZKR_CUDA(cudaMalloc(&dout, 64));
+    ZKR_CUDA(cudaMalloc(&dout, 1024));
     cudaEvent_t e0, e1;
     ZKR_CUDA(cudaEventCreate(&e0));
     ZKR_CUDA(cudaEventCreate(&e1));
@@ -350,11 +377,18 @@ extern "C" int zkr_microbench(zkr_ctx* ctx, int which, int iters, double* ops_pe
                 ZKR_LAUNCH(ctx, k_bench_batch_affine<16>, ctx->sm_count * 3, 128, 16 * 32 * 128, ctx->s[0], dout, iters);
                 per_thread = 16.0 * iters * (ctx->sm_count * 3.0 * 128) / ((double)threads * blocks); break;
             }
-            default: {                                      // 11: B = 64 per inversion, 64-thread CTAs
+            case 12: ZKR_LAUNCH(ctx, (k_bench_madd_v<Fq, true>), blocks, threads, 0, ctx->s[0], dout, iters);
+                per_thread = 1.0 * iters; break;
+            case 13: ZKR_LAUNCH(ctx, (k_bench_madd_v<Fq2, false>), ctx->sm_count * 2, 128, 0, ctx->s[0], dout, iters);
+                per_thread = 1.0 * iters * (ctx->sm_count * 2.0 * 128) / ((double)threads * blocks); break;   // 8 warps / SM, as in the MSM
+            case 14: ZKR_LAUNCH(ctx, (k_bench_madd_v<Fq2, true>), ctx->sm_count * 2, 128, 0, ctx->s[0], dout, iters);
+                per_thread = 1.0 * iters * (ctx->sm_count * 2.0 * 128) / ((double)threads * blocks); break;
+            case 11: {                                      // B = 64 per inversion, 64-thread CTAs
                 ZKR_CUDA(cudaFuncSetAttribute(k_bench_batch_affine<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 32 * 64));
                 ZKR_LAUNCH(ctx, k_bench_batch_affine<64>, ctx->sm_count, 64, 64 * 32 * 64, ctx->s[0], dout, iters);
                 per_thread = 64.0 * iters * (ctx->sm_count * 64.0) / ((double)threads * blocks); break;
             }
+            default: break;
         }
         ZKR_CUDA(cudaEventRecord(e1, ctx->s[0]));
         ZKR_CUDA(cudaEventSynchronize(e1));

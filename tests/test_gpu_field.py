@@ -35,7 +35,11 @@ def test_field_ops(zctx, field, p):
            2: [(x - y) % p for x, y in zip(a, b)],
            3: [x * x * rinv % p for x in a],
            5: [x * MONT % p for x in a],
-           6: [x * rinv % p for x in a]}
+           6: [x * rinv % p for x in a],
+           # sums of products with one reduction (fp.cuh mont_mul2_raw / mont_mul4_raw; the lazily reduced additions use them)
+           7: [(x * y + (x + y) * (x - y)) * rinv % p for x, y in zip(a, b)],
+           8: [(x * y - (x + y) * (x - y)) * rinv % p for x, y in zip(a, b)],
+           9: [(x * y + (x + y) * (x - y) + x * (x - y) + (x + y) * y) * rinv % p for x, y in zip(a, b)]}
     for op, e in exp.items():
         _lib.check(L.zkr_test_field_op(zctx, field, op, _lib.buf_ptr(A), _lib.buf_ptr(B), _lib.buf_ptr(out), n))
         got = unpack(out)
@@ -87,6 +91,15 @@ def test_curve_ops(zctx, group):
     assert up(out) == [cur.add(p, p) for p in P]
     _lib.check(L.zkr_test_curve_op(zctx, group, 3, _lib.buf_ptr(Pa), _lib.buf_ptr(Qa), _lib.buf_ptr(out), n))
     assert up(out) == [cur.add(cur.add(p, p), cur.add(q, q)) for p, q in zip(P, Q)]
+    # 2P + Q through the mixed addition, plain and lazily reduced (Q == 2P and Q == -2P are its exceptional branches)
+    Q2 = list(Q)
+    Q2[5] = cur.add(P[5], P[5])
+    Q2[6] = cur.neg(cur.add(P[6], P[6]))
+    Q2a = pk(Q2)
+    want = [cur.add(cur.add(p, p), q) for p, q in zip(P, Q2)]
+    for op in (4, 5):
+        _lib.check(L.zkr_test_curve_op(zctx, group, op, _lib.buf_ptr(Pa), _lib.buf_ptr(Q2a), _lib.buf_ptr(out), n))
+        assert up(out) == want, "curve op %d" % op
     ks = [0, 1, 2, bn.R - 1, bn.R, (1 << 256) - 1] + [rng.randrange(bn.R) for _ in range(n - 6)]
     K = pack(ks)
     _lib.check(L.zkr_test_curve_op(zctx, group, 2, _lib.buf_ptr(Pa), _lib.buf_ptr(K), _lib.buf_ptr(out), n))
@@ -97,6 +110,6 @@ def test_microbench_runs(zctx):
     L = _lib.lib()
     ops = C.c_double()
     ms = C.c_float()
-    for which, it in ((0, 20000), (1, 20000), (2, 2000), (3, 500)):
+    for which, it in ((0, 20000), (1, 20000), (2, 2000), (3, 500), (12, 500), (13, 200), (14, 200)):
         _lib.check(L.zkr_microbench(zctx, which, it, C.byref(ops), C.byref(ms)))
         assert ops.value > 0

@@ -14,6 +14,19 @@ pytestmark = pytest.mark.gpu
 R = bn.R
 
 
+@pytest.fixture(params=[0, 3], ids=["madd", "madd_lazy"])
+def lazy(request):
+    """Both forms of the bucket accumulation's mixed addition (ZKR_LAZY is read on every MSM call; csrc/msm.cuh)."""
+    import os
+    old = os.environ.get("ZKR_LAZY")
+    os.environ["ZKR_LAZY"] = str(request.param)
+    yield request.param
+    if old is None:
+        del os.environ["ZKR_LAZY"]
+    else:
+        os.environ["ZKR_LAZY"] = old
+
+
 def load_bases(zctx, group, pts, c=0):
     L = _lib.lib()
     arr = pack_g1(pts) if group == 1 else pack_g2(pts)
@@ -55,7 +68,7 @@ def scalar_sets(rng, n):
 
 @pytest.mark.parametrize("group,n,c", [(1, 1, 0), (1, 2, 4), (1, 37, 0), (1, 300, 5), (1, 300, 13), (1, 1500, 0),
                                        (2, 1, 0), (2, 41, 4), (2, 200, 0), (2, 200, 11)])
-def test_msm_small(zctx, group, n, c):
+def test_msm_small(zctx, group, n, c, lazy):
     L = _lib.lib()
     rng = random.Random(1000 * group + n + c)
     fb = bn.fixed_base(group)
@@ -82,7 +95,7 @@ def test_msm_small(zctx, group, n, c):
 
 
 @pytest.mark.parametrize("group,n", [(1, 30000), (2, 6000)])
-def test_msm_arithmetic_progression(zctx, group, n):
+def test_msm_arithmetic_progression(zctx, group, n, lazy):
     """P_i = (a0 + i d) G  =>  sum k_i P_i = (sum k_i (a0 + i d) mod r) G   (SURVEY 8(d) config 3 check)."""
     L = _lib.lib()
     rng = random.Random(77 + group)
