@@ -112,7 +112,11 @@ def main():
     s = open(path).read()
     head = "## 6. Results table"
     i = s.index(head)
-    s = s[:i] + ("## 6. Results table (filled by `tools/fill_results.py` from the JSON records under `profiles/`, round 2)\n\n" + table)
+    note = ("\nRecords of the final round-2 code (lazily reduced additions, task-aware sharded proof): `r02_bench_n1.json`, "
+            "`r02_bench_n2.json`, `r02_bench_tx_n1.json`, `r02_bench_withdraw_n1.json`.  The 4- and 8-GPU files and the single-GPU "
+            "sweep were taken before that last arithmetic change (accumulation 6 % (G1) / 19 % (G2) slower than now); the driver's "
+            "round-end scaling record carries their final values.\n")
+    s = s[:i] + ("## 6. Results table (filled by `tools/fill_results.py` from the JSON records under `profiles/`, round 2)\n\n" + table + note)
     open(path, "w").write(s)
     print(table)
 
