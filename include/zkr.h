@@ -342,12 +342,13 @@ int zkr_synth_points(zkr_ctx* ctx, int group, const void* scalars, size_t n, voi
 
 /* ---- test hooks (element-wise field / curve kernels; used by the parity tests) --------- */
 /* field: 0 = Fq, 1 = Fr.  op: 0 mul, 1 add, 2 sub, 3 sqr, 4 inverse, 5 to_mont, 6 from_mont; sums of products with one
- * reduction: 7 = a b + (a+b)(a-b), 8 = a b - (a+b)(a-b), 9 = a b + (a+b)(a-b) + a (a-b) + (a+b) b.
+ * reduction: 7 = a b + (a+b)(a-b), 8 = a b - (a+b)(a-b), 9 = a b + (a+b)(a-b) + a (a-b) + (a+b) b; 10 = the dedicated
+ * squaring (100 instead of 128 wide multiplies).
  * a, b, out: n x 32 B host buffers (Montgomery form operands for mul/add/sub/sqr/inverse/sums of products). */
 int zkr_test_field_op(zkr_ctx* ctx, int field, int op, const void* a, const void* b, void* out, size_t n);
 /* group 1/2.  op: 0 = affine+affine (via XYZZ mixed add), 1 = double, 2 = scalar mul by k[i] (32 B std),
- * 3 = 2P + 2Q through the full XYZZ add (both operands with non-trivial zz), 4 / 5 = 2P + Q through the mixed addition in
- * its plain / lazily reduced form (non-trivial zz).  Points: affine Montgomery, x == 0 = infinity; out affine Montgomery. */
+ * 3 = 2P + 2Q through the full XYZZ add (both operands with non-trivial zz), 4 / 5 / 6 = 2P + Q through the mixed addition in
+ * its plain / lazily reduced / lazily reduced + dedicated-squaring form (non-trivial zz).  Points: affine Montgomery, x == 0 = infinity; out affine Montgomery. */
 int zkr_test_curve_op(zkr_ctx* ctx, int group, int op, const void* p, const void* q_or_k, void* out, size_t n);
 /* white-box: copy an internal MSM work buffer of `b` to the host (what: 0 table, 1/2 keys, 3/4 vals,
  * 5 buckets, 6 result, 7 reduce partials, 8/9 boundary keys, 10/11 boundary partials). */
@@ -357,7 +358,7 @@ int zkr_test_bases_peek(const zkr_bases* b, int what, size_t offset, void* out, 
  * add pairs, 7 = 64-bit add chain; 8 = Fermat inversions, 9 = binary-Euclid inversions (full grids), 10 / 11 =
  * batched-affine additions with one inversion per thread and 16 / 64 additions (the measurement behind the
  * "batched affine" entry of DESIGN.md 4.8); 12 = lazily reduced G1 mixed-add chain, 13 / 14 = G2 mixed-add chain in its
- * plain / lazily reduced form at the MSM's 8 warps per SM.  Returns operations per second (IMADs / modmuls / madds / pairs /
+ * plain / lazily reduced form at the MSM's 8 warps per SM, 15 = 12 with the dedicated squaring.  Returns operations per second (IMADs / modmuls / madds / pairs /
  * inversions / additions). */
 int zkr_microbench(zkr_ctx* ctx, int which, int iters, double* ops_per_s, float* ms);
 

@@ -35,9 +35,10 @@
 namespace zkr {
 
 constexpr int kAccumThreads = 128;
-// Which groups accumulate with XYZZ::madd_lazy (bit 0 G1, bit 1 G2; ZKR_LAZY overrides, A/B knob).  Measured on a B200
-// (profiles/r02_lazy_reduction_ab.json): G1 launch 1.91 -> 1.80 ms, 2^20 proof 16.79 -> 15.54 ms (15.34 with the tails).
-constexpr int kLazyDefault = 3;
+// Which groups accumulate with XYZZ::madd_lazy (bit 0 G1, bit 1 G2) and whether G1 squares with mont_sqr_raw (bit 2);
+// ZKR_LAZY overrides (A/B knob).  Measured on a B200 (profiles/r02_lazy_reduction_ab.json, r02_fast_sqr_ab.json): G1 launch
+// 1.91 -> 1.80 -> 1.73 ms, 2^20 proof 16.79 -> 15.34 -> 15.08 ms.
+constexpr int kLazyDefault = 7;
 constexpr int kLevelLog = 4;          // boundary levels: 16 entries per thread ...
 constexpr int kLevelLogBig = 2;       // ... except while the list is long: 4 per thread keeps ~4x more warps in flight
 constexpr size_t kLevelBigMin = 1u << 16;
@@ -132,7 +133,7 @@ static __global__ void k_digits(const uint32_t* __restrict__ scalars, const uint
 // that sees a key change owns that boundary; the boundary at a chunk's first entry is found by reading the previous
 // chunk's last key.  k_bucket_gather turns the head / tail partials into bucket sums with these bounds in ONE launch.
 // LAZY: the mixed addition with sums of products reduced once (XYZZ::madd_lazy; same words out).
-template <class F, bool PREFETCH, bool LAZY>
+template <class F, bool PREFETCH, int LAZY>      // LAZY 2: madd_lazy with the dedicated squaring (fp.cuh mont_sqr_raw)
 __global__ void __launch_bounds__(kAccumThreads, sizeof(F) == 32 ? 4 : 2)       // G1: 128 registers, 4 CTAs / SM
 k_accum_affine(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint32_t total, int logL,
                const char* __restrict__ table, XYZZ<F>* __restrict__ buckets, XYZZ<F>* __restrict__ bnd,
@@ -202,7 +203,8 @@ k_accum_affine(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ v
             cur = key;
         }
         if (v & kNegBit) p.y = p.y.neg();
-        if (LAZY) acc.madd_lazy(p);
+        if (LAZY == 2) acc.template madd_lazy<true>(p);
+        else if (LAZY == 1) acc.template madd_lazy<false>(p);
         else acc.madd(p);
     }
     if (cur < sentinel) {
@@ -729,8 +731,10 @@ int bases_build(zkr_ctx* ctx, zkr_bases* b, const char* h_points, size_t n_src, 
     ZKR_CUDA(cudaFuncSetAttribute((k_bucket_sums<F, kReduceThreads>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(XB * kReduceThreads)));
     ZKR_CUDA(cudaFuncSetAttribute((k_bucket_weighted<F, kReduceThreads>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(XB * kReduceThreads)));
     constexpr bool kPrefetch = sizeof(F) == 32;
-    ZKR_CUDA(cudaFuncSetAttribute((k_accum_affine<F, kPrefetch, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
-    ZKR_CUDA(cudaFuncSetAttribute((k_accum_affine<F, kPrefetch, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+    ZKR_CUDA(cudaFuncSetAttribute((k_accum_affine<F, kPrefetch, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+    ZKR_CUDA(cudaFuncSetAttribute((k_accum_affine<F, kPrefetch, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+    if (sizeof(F) == 32)
+        ZKR_CUDA(cudaFuncSetAttribute((k_accum_affine<F, kPrefetch, sizeof(F) == 32 ? 2 : 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
     ZKR_CUDA(cudaFuncSetAttribute(k_bucket_gather<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(XB * kGatherThreads)));
     ZKR_CUDA(cudaStreamSynchronize(st));
     return ZKR_OK;
@@ -786,18 +790,21 @@ int msm_run(zkr_ctx* ctx, cudaStream_t st, const zkr_bases* b, const uint32_t* d
     static const int force_levels = getenv("ZKR_MSM_LEVELS") ? atoi(getenv("ZKR_MSM_LEVELS")) : -1;
     const bool use_levels = force_levels >= 0 ? force_levels != 0 : c > 20;
     if (!use_levels) ZKR_CUDA(cudaMemsetAsync(wk.run_lo, 0xff, 4 * (size_t)nb, st));
-    // ZKR_LAZY: bit 0 = G1, bit 1 = G2 use the lazily reduced mixed addition (A/B knob; bit-identical results)
+    // ZKR_LAZY: bit 0 = G1, bit 1 = G2 use the lazily reduced mixed addition, bit 2 = G1 additionally squares with
+    // mont_sqr_raw (A/B knob; bit-identical results)
     const char* lazy_env = getenv("ZKR_LAZY");             // read per call: the GPU tests flip it inside one process
     const int lazy_mask = lazy_env ? atoi(lazy_env) : kLazyDefault;
-    if (lazy_mask & (sizeof(F) == 32 ? 1 : 2)) {
-        ZKR_LAUNCH(ctx, (k_accum_affine<F, kPrefetch, true>), b->T1p / kAccumThreads, kAccumThreads, smem, st, skeys, svals,
-                   total, b->logL, b->table, buckets, (XYZZ<F>*)wk.bnd[0], use_levels ? wk.bnd_keys[0] : nullptr, nb,
-                   use_levels ? nullptr : wk.run_lo);
-    } else {
-        ZKR_LAUNCH(ctx, (k_accum_affine<F, kPrefetch, false>), b->T1p / kAccumThreads, kAccumThreads, smem, st, skeys, svals,
-                   total, b->logL, b->table, buckets, (XYZZ<F>*)wk.bnd[0], use_levels ? wk.bnd_keys[0] : nullptr, nb,
-                   use_levels ? nullptr : wk.run_lo);
-    }
+    const int variant = !(lazy_mask & (sizeof(F) == 32 ? 1 : 2)) ? 0 : (sizeof(F) == 32 && (lazy_mask & 4)) ? 2 : 1;
+    auto launch = [&](auto kern) -> int {
+        ZKR_LAUNCH(ctx, kern, b->T1p / kAccumThreads, kAccumThreads, smem, st, skeys, svals, total, b->logL, b->table, buckets,
+                   (XYZZ<F>*)wk.bnd[0], use_levels ? wk.bnd_keys[0] : nullptr, nb, use_levels ? nullptr : wk.run_lo);
+        return ZKR_OK;
+    };
+    int lrc;
+    if (variant == 2) lrc = launch(k_accum_affine<F, kPrefetch, sizeof(F) == 32 ? 2 : 1>);
+    else if (variant == 1) lrc = launch(k_accum_affine<F, kPrefetch, 1>);
+    else lrc = launch(k_accum_affine<F, kPrefetch, 0>);
+    if (lrc != ZKR_OK) return lrc;
     ctx->prof_end(sizeof(F) == 32 ? PROF_ACCUM_G1 : PROF_ACCUM_G2, pslot, st);
     if (hooks && hooks->ev_accum) ZKR_CUDA(cudaEventRecord(hooks->ev_accum, st));
     if (!use_levels) {

@@ -26,6 +26,7 @@ __global__ void k_field_op(int op, const uint32_t* a, const uint32_t* b, uint32_
         case 6: r = x.from_mont(); break;
         case 7: r = F::mul2(x, y, x + y, x - y); break;      // x y + (x + y)(x - y), one reduction (fp.cuh mont_mul2_raw)
         case 8: r = F::msub(x, y, x + y, x - y); break;      // x y - (x + y)(x - y)
+        case 10: r = x.sqr_fast(); break;                    // the dedicated squaring (fp.cuh mont_sqr_raw)
         default: {                                           // 9: four products x y + (x+y)(x-y) + x (x-y) + (x+y) y
             F s = x + y, d = x - y;
             mont_mul4_raw<typename F::Params>(r.v, x.v, y.v, s.v, d.v, x.v, d.v, s.v, y.v);
@@ -59,7 +60,8 @@ __global__ void k_curve_op(int op, const char* p, const char* q, char* out, size
         acc = acc.dbl();
         if (!Q.is_inf()) {
             if (op == 4) acc.madd(Q);
-            else acc.madd_lazy(Q);
+            else if (op == 5) acc.madd_lazy(Q);
+            else acc.template madd_lazy<true>(Q);
         }
     }
     acc.to_affine().store(out + AB * i);
@@ -125,14 +127,15 @@ __global__ void k_bench_madd(uint32_t* out, int iters) {
 }
 
 // 12 / 13 / 14: register-resident chains of the lazily reduced G1 addition and of the G2 addition in both forms
-template <class F, bool LAZY>
+template <class F, int LAZY>
 __global__ void k_bench_madd_v(uint32_t* out, int iters) {
     Affine<F> g;
     g.x = F::one();
     g.y = F::one().dbl();
     XYZZ<F> acc = XYZZ<F>::dbl_affine(g);
     for (int it = 0; it < iters; it++) {
-        if (LAZY) acc.madd_lazy(g);
+        if (LAZY == 2) acc.template madd_lazy<true>(g);
+        else if (LAZY == 1) acc.template madd_lazy<false>(g);
         else acc.madd(g);
     }
     if (acc.is_inf()) acc.store(out + 64);   // never true for this chain; keeps the additions live
@@ -290,8 +293,8 @@ __global__ void k_bench_iadd64(uint32_t* out, int iters, unsigned long long a) {
 }  // namespace
 
 extern "C" int zkr_test_field_op(zkr_ctx* ctx, int field, int op, const void* a, const void* b, void* out, size_t n) {
-    if (!ctx || !a || !out || n == 0 || op < 0 || op > 9 || (field != 0 && field != 1)) return ZKR_E_INVALID;
-    if ((op <= 2 || op >= 7) && !b) return ZKR_E_INVALID;
+    if (!ctx || !a || !out || n == 0 || op < 0 || op > 10 || (field != 0 && field != 1)) return ZKR_E_INVALID;
+    if ((op <= 2 || (op >= 7 && op <= 9)) && !b) return ZKR_E_INVALID;
     DeviceGuard g(ctx->device);
     uint32_t *da = nullptr, *db = nullptr, *dout = nullptr;
     ZKR_CUDA(cudaMalloc(&da, n * 32));
@@ -313,7 +316,7 @@ extern "C" int zkr_test_field_op(zkr_ctx* ctx, int field, int op, const void* a,
 }
 
 extern "C" int zkr_test_curve_op(zkr_ctx* ctx, int group, int op, const void* p, const void* q, void* out, size_t n) {
-    if (!ctx || !p || !out || n == 0 || op < 0 || op > 5 || (group != 1 && group != 2)) return ZKR_E_INVALID;
+    if (!ctx || !p || !out || n == 0 || op < 0 || op > 6 || (group != 1 && group != 2)) return ZKR_E_INVALID;
     if (op != 1 && !q) return ZKR_E_INVALID;
     DeviceGuard g(ctx->device);
     size_t ab = group == 1 ? 64 : 128;
@@ -338,7 +341,7 @@ extern "C" int zkr_test_curve_op(zkr_ctx* ctx, int group, int op, const void* p,
 }
 
 extern "C" int zkr_microbench(zkr_ctx* ctx, int which, int iters, double* ops_per_s, float* ms_out) {
-    if (!ctx || which < 0 || which > 14 || iters <= 0 || !ops_per_s) return ZKR_E_INVALID;
+    if (!ctx || which < 0 || which > 15 || iters <= 0 || !ops_per_s) return ZKR_E_INVALID;
     DeviceGuard g(ctx->device);
     uint32_t* dout = nullptr;
     ZKR_CUDA(cudaMalloc(&dout, 1024));
@@ -377,11 +380,13 @@ extern "C" int zkr_microbench(zkr_ctx* ctx, int which, int iters, double* ops_pe
                 ZKR_LAUNCH(ctx, k_bench_batch_affine<16>, ctx->sm_count * 3, 128, 16 * 32 * 128, ctx->s[0], dout, iters);
                 per_thread = 16.0 * iters * (ctx->sm_count * 3.0 * 128) / ((double)threads * blocks); break;
             }
-            case 12: ZKR_LAUNCH(ctx, (k_bench_madd_v<Fq, true>), blocks, threads, 0, ctx->s[0], dout, iters);
+            case 12: ZKR_LAUNCH(ctx, (k_bench_madd_v<Fq, 1>), blocks, threads, 0, ctx->s[0], dout, iters);
                 per_thread = 1.0 * iters; break;
-            case 13: ZKR_LAUNCH(ctx, (k_bench_madd_v<Fq2, false>), ctx->sm_count * 2, 128, 0, ctx->s[0], dout, iters);
+            case 15: ZKR_LAUNCH(ctx, (k_bench_madd_v<Fq, 2>), blocks, threads, 0, ctx->s[0], dout, iters);
+                per_thread = 1.0 * iters; break;
+            case 13: ZKR_LAUNCH(ctx, (k_bench_madd_v<Fq2, 0>), ctx->sm_count * 2, 128, 0, ctx->s[0], dout, iters);
                 per_thread = 1.0 * iters * (ctx->sm_count * 2.0 * 128) / ((double)threads * blocks); break;   // 8 warps / SM, as in the MSM
-            case 14: ZKR_LAUNCH(ctx, (k_bench_madd_v<Fq2, true>), ctx->sm_count * 2, 128, 0, ctx->s[0], dout, iters);
+            case 14: ZKR_LAUNCH(ctx, (k_bench_madd_v<Fq2, 1>), ctx->sm_count * 2, 128, 0, ctx->s[0], dout, iters);
                 per_thread = 1.0 * iters * (ctx->sm_count * 2.0 * 128) / ((double)threads * blocks); break;
             case 11: {                                      // B = 64 per inversion, 64-thread CTAs
                 ZKR_CUDA(cudaFuncSetAttribute(k_bench_batch_affine<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 32 * 64));

@@ -30,6 +30,7 @@ static void field_ops(int op, const uint32_t* a, const uint32_t* b, const uint32
             case 4: r = F::msub(A, B, Cc, D); break;          // a b - c d
             case 5: r = A.neg_lazy(); break;                  // p - a in (0, p]
             case 6: r = A.sqr(); break;
+            case 8: r = A.sqr_fast(); break;                  // mont_sqr_raw
             default: {                                        // 7: four products a b + c d + a d + c b
                 mont_mul4_raw<typename std::conditional<std::is_same<F, Fq>::value, FqParams, FrParams>::type>(
                     r.v, A.v, B.v, Cc.v, D.v, A.v, D.v, Cc.v, B.v);
@@ -67,7 +68,8 @@ static void madd_ops(int lazy, const uint32_t* acc, const uint32_t* pt, uint32_t
     for (int k = 0; k < n; k++) {
         XYZZ<F> A = XYZZ<F>::load(acc + 4 * W * k);
         Affine<F> P = Affine<F>::load(pt + 2 * W * k);
-        if (lazy) A.madd_lazy(P);
+        if (lazy == 2) A.template madd_lazy<true>(P);
+        else if (lazy) A.template madd_lazy<false>(P);
         else A.madd(P);
         A.store(out + 4 * W * k);
     }

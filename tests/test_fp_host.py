@@ -65,9 +65,18 @@ def test_field_ops_match_python(lib, field, p):
         3: lambda a, b, c, d: (a * b + c * d) * rinv % p,
         4: lambda a, b, c, d: (a * b - c * d) * rinv % p,
         6: lambda a, b, c, d: a * a * rinv % p,
+        8: lambda a, b, c, d: a * a * rinv % p,          # the dedicated squaring (operands < 2^254 by contract: see below)
         7: lambda a, b, c, d: (a * b + c * d + a * d + c * b) * rinv % p,
     }
     for op, f in exp.items():
+        if op == 8:      # mont_sqr_raw doubles its operand inside 256 bits: canonical operands (< p < 2^254) only
+            A8 = pack([t[0] % p for t in tup])
+            lib.fp_host_op(field, op, ptr(A8), ptr(B), ptr(Cc), ptr(D), ptr(out), n)
+            assert lib.fp_host_carry_lost() == 0
+            got = unpack(out)
+            bad = [i for i in range(n) if got[i] != f(tup[i][0] % p, 0, 0, 0)]
+            assert not bad, "field %d sqr_fast: first mismatch at %d %s" % (field, bad[0], hex(tup[bad[0]][0]))
+            continue
         lib.fp_host_op(field, op, ptr(A), ptr(B), ptr(Cc), ptr(D), ptr(out), n)
         assert lib.fp_host_carry_lost() == 0, "op %d: a carry the code calls impossible occurred" % op
         got = unpack(out)
@@ -167,6 +176,10 @@ def test_madd_lazy_is_bit_identical_and_correct(lib, group):
     lib.xyzz_host_madd(group, 1, ptr(ACC), ptr(PT), ptr(o1), n)
     assert lib.fp_host_carry_lost() == 0
     assert o0.tobytes() == o1.tobytes(), "madd_lazy differs from madd"
+    o2 = np.zeros_like(o0)
+    lib.xyzz_host_madd(group, 2, ptr(ACC), ptr(PT), ptr(o2), n)
+    assert lib.fp_host_carry_lost() == 0
+    assert o0.tobytes() == o2.tobytes(), "madd_lazy with the dedicated squaring differs from madd"
     # against the oracle: x = X / ZZ, y = Y / ZZZ
     rinv = pow(MONT, -1, p)
     vals = [v * rinv % p for v in unpack(o1)]

@@ -39,7 +39,8 @@ def test_field_ops(zctx, field, p):
            # sums of products with one reduction (fp.cuh mont_mul2_raw / mont_mul4_raw; the lazily reduced additions use them)
            7: [(x * y + (x + y) * (x - y)) * rinv % p for x, y in zip(a, b)],
            8: [(x * y - (x + y) * (x - y)) * rinv % p for x, y in zip(a, b)],
-           9: [(x * y + (x + y) * (x - y) + x * (x - y) + (x + y) * y) * rinv % p for x, y in zip(a, b)]}
+           9: [(x * y + (x + y) * (x - y) + x * (x - y) + (x + y) * y) * rinv % p for x, y in zip(a, b)],
+           10: [x * x * rinv % p for x in a]}                      # the dedicated squaring (mont_sqr_raw)
     for op, e in exp.items():
         _lib.check(L.zkr_test_field_op(zctx, field, op, _lib.buf_ptr(A), _lib.buf_ptr(B), _lib.buf_ptr(out), n))
         got = unpack(out)
@@ -97,7 +98,7 @@ def test_curve_ops(zctx, group):
     Q2[6] = cur.neg(cur.add(P[6], P[6]))
     Q2a = pk(Q2)
     want = [cur.add(cur.add(p, p), q) for p, q in zip(P, Q2)]
-    for op in (4, 5):
+    for op in (4, 5, 6):
         _lib.check(L.zkr_test_curve_op(zctx, group, op, _lib.buf_ptr(Pa), _lib.buf_ptr(Q2a), _lib.buf_ptr(out), n))
         assert up(out) == want, "curve op %d" % op
     ks = [0, 1, 2, bn.R - 1, bn.R, (1 << 256) - 1] + [rng.randrange(bn.R) for _ in range(n - 6)]
@@ -110,6 +111,6 @@ def test_microbench_runs(zctx):
     L = _lib.lib()
     ops = C.c_double()
     ms = C.c_float()
-    for which, it in ((0, 20000), (1, 20000), (2, 2000), (3, 500), (12, 500), (13, 200), (14, 200)):
+    for which, it in ((0, 20000), (1, 20000), (2, 2000), (3, 500), (12, 500), (13, 200), (14, 200), (15, 500)):
         _lib.check(L.zkr_microbench(zctx, which, it, C.byref(ops), C.byref(ms)))
         assert ops.value > 0

@@ -14,17 +14,28 @@ pytestmark = pytest.mark.gpu
 R = bn.R
 
 
-@pytest.fixture(params=[0, 3], ids=["madd", "madd_lazy"])
-def lazy(request):
-    """Both forms of the bucket accumulation's mixed addition (ZKR_LAZY is read on every MSM call; csrc/msm.cuh)."""
+def _with_lazy(value):
     import os
     old = os.environ.get("ZKR_LAZY")
-    os.environ["ZKR_LAZY"] = str(request.param)
-    yield request.param
+    os.environ["ZKR_LAZY"] = str(value)
+    yield value
     if old is None:
         del os.environ["ZKR_LAZY"]
     else:
         os.environ["ZKR_LAZY"] = old
+
+
+@pytest.fixture(params=[0, 7], ids=["madd", "madd_lazy_sqr"])
+def lazy(request):
+    """The round-1 form and the default form of the bucket accumulation's mixed addition (ZKR_LAZY is read on every MSM
+    call; csrc/msm.cuh): 0 = plain, 7 = sums of products reduced once + dedicated squaring."""
+    yield from _with_lazy(request.param)
+
+
+@pytest.fixture
+def lazy_intermediate():
+    """3 = sums of products reduced once, generic squaring (the A/B's middle arm stays selectable, so it stays tested)"""
+    yield from _with_lazy(3)
 
 
 def load_bases(zctx, group, pts, c=0):
@@ -92,6 +103,20 @@ def test_msm_small(zctx, group, n, c, lazy):
             msm(zctx, group, h, bad)
         assert ei.value.code == -3
     L.zkr_bases_free(h)
+
+
+@pytest.mark.parametrize("group,n", [(1, 3000), (2, 800)])
+def test_msm_intermediate_accumulation_form(zctx, group, n, lazy_intermediate):
+    rng = random.Random(5 + group)
+    a0, d = rng.randrange(R), rng.randrange(R)
+    fb = bn.fixed_base(group)
+    pts = fb.mul_many([(a0 + i * d) % R for i in range(n)])
+    h = load_bases(zctx, group, pts)
+    for name in ("uniform", "rollup_like", "all_equal"):
+        sc = scalar_sets(rng, n)[name]
+        e = sum(k * (a0 + i * d) for i, k in enumerate(sc)) % R
+        assert msm(zctx, group, h, sc) == fb.mul_many([e])[0], name
+    _lib.lib().zkr_bases_free(h)
 
 
 @pytest.mark.parametrize("group,n", [(1, 30000), (2, 6000)])

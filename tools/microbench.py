@@ -20,7 +20,7 @@ for name, which, iters in (("imad_per_s", 0, 100000), ("imad_wide_per_s", 1, 100
                            ("fq_inverse_fermat_per_s", 8, 40), ("fq_inverse_euclid_full_grid_per_s", 9, 40),
                            ("g1_batch_affine_add_b16_per_s", 10, 60), ("g1_batch_affine_add_b64_per_s", 11, 30),
                            ("g1_madd_lazy_per_s", 12, 3000), ("g2_madd_8warps_per_s", 13, 1000),
-                           ("g2_madd_lazy_8warps_per_s", 14, 1000)):
+                           ("g2_madd_lazy_8warps_per_s", 14, 1000), ("g1_madd_lazy_sqr_per_s", 15, 3000)):
     ops, ms = C.c_double(), C.c_float()
     _lib.check(L.zkr_microbench(h, which, iters, C.byref(ops), C.byref(ms)))
     res[name] = ops.value
@@ -32,6 +32,7 @@ res["fermat_inverse_in_modmuls"] = res["fq_modmul_per_s"] / res["fq_inverse_ferm
 res["euclid_inverse_in_modmuls_full_grid"] = res["fq_modmul_per_s"] / res["fq_inverse_euclid_full_grid_per_s"]
 res["batch_affine_b16_vs_madd"] = res["g1_batch_affine_add_b16_per_s"] / res["g1_madd_per_s"]
 res["batch_affine_b64_vs_madd"] = res["g1_batch_affine_add_b64_per_s"] / res["g1_madd_per_s"]
+res["g1_madd_lazy_sqr_vs_madd"] = res["g1_madd_lazy_sqr_per_s"] / res["g1_madd_per_s"]
 res["g1_madd_lazy_vs_madd"] = res["g1_madd_lazy_per_s"] / res["g1_madd_per_s"]
 res["g2_madd_lazy_vs_madd"] = res["g2_madd_lazy_8warps_per_s"] / res["g2_madd_8warps_per_s"]
 os.makedirs("gpurun_out", exist_ok=True)
