@@ -112,10 +112,11 @@ def main():
     s = open(path).read()
     head = "## 6. Results table"
     i = s.index(head)
-    note = ("\nRecords of the final round-2 code (lazily reduced additions, task-aware sharded proof): `r02_bench_n1.json`, "
-            "`r02_bench_n2.json`, `r02_bench_tx_n1.json`, `r02_bench_withdraw_n1.json`.  The 4- and 8-GPU files and the single-GPU "
-            "sweep were taken before that last arithmetic change (accumulation 6 % (G1) / 19 % (G2) slower than now); the driver's "
-            "round-end scaling record carries their final values.\n")
+    note = ("\nRecord of the final round-2 code (lazily reduced additions + dedicated squaring, task-aware sharded proof): "
+            "`r02_bench_n1.json`.  `r02_bench_n2.json`, `r02_bench_tx_n1.json` and `r02_bench_withdraw_n1.json` have the lazily reduced "
+            "additions but predate the dedicated squaring (G1 accumulation 3.7 % slower than now); the 4- and 8-GPU files and the "
+            "single-GPU sweep predate both (accumulation 10 % (G1) / 19 % (G2) slower than now); the driver's round-end scaling "
+            "record carries their final values.\n")
     s = s[:i] + ("## 6. Results table (filled by `tools/fill_results.py` from the JSON records under `profiles/`, round 2)\n\n" + table + note)
     open(path, "w").write(s)
     print(table)
