@@ -47,6 +47,14 @@ def operands(p, rng, n):
     """n operand 4-tuples: the corners first (0, 1, p - 1 and the non-canonical p the lazy negation can produce), then random"""
     corner = [0, 1, 2, p - 1, p - 2, p, (p + 1) // 2, MONT % p, (1 << 253)]
     tup = [(a, b, c, d) for a in (0, 1, p - 1, p) for b in (0, p - 1, p) for c in (0, p - 1, p) for d in (1, p - 1, p)]
+    # limb patterns: carries between limbs, the bit the squaring's doubled operand moves from limb i into limb i + 1
+    pat = (0, 1, 0x7fffffff, 0x80000000, 0xffffffff, 0xfffffffe, 0x80000001)
+
+    def patterned():
+        limbs = [rng.choice(pat) for _ in range(7)] + [rng.choice((0, 1, 0x10000000, 0x30644e71))]
+        return sum(l << (32 * i) for i, l in enumerate(limbs))      # top limb below the moduli's: the value is < p
+    for _ in range(3000):
+        tup.append(tuple(patterned() for _ in range(4)))
     while len(tup) < n:
         tup.append(tuple(rng.choice(corner) if rng.random() < 0.15 else rng.randrange(p) for _ in range(4)))
     return tup[:n]
